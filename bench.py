@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - graph-steps/sec of the batched ChebConv forward (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): one ChebConv layer, K=5, 32 -> 32 features, bias +
+leaky_relu, over a batch of 1024 Barabasi-Albert (m=2) graphs of 20..110 nodes.  A "step" is
+one pass of the hot path over one such batch.  Weak scaling: every rank gets its own 1024 graphs.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20           # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1      # the CPU restatement of the reference path
+    torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU
+
+Timing: CUDA events on the launching stream around exactly K back-to-back steps, barrier +
+synchronize on both sides, max over ranks.  L2 hygiene: the timed loop rotates over R distinct
+copies of the whole input/output set with R * bytes > 2 * 126 MB, so no step finds its inputs in L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "graph-steps/sec (ChebConv K=5 fwd, BA 20-110 nodes)"
+UNIT = "graph-steps/s"
+L2_BYTES = 126 * 1024 * 1024
+SIZES = np.arange(20, 111, 10)
+
+
+# --------------------------------------------------------------------------------------------
+# workload (pure numpy/networkx; shared by both arms)
+# --------------------------------------------------------------------------------------------
+def ba_csr(n, seed):
+    """CSR of networkx.barabasi_albert_graph(n, 2, seed) (generator of src/offloading_v3.py:40)."""
+    import networkx as nx
+    g = nx.barabasi_albert_graph(int(n), 2, seed=int(seed))
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    cols = []
+    for i in range(n):
+        nb = sorted(g.adj[i])
+        cols.append(np.asarray(nb, dtype=np.int64))
+        indptr[i + 1] = indptr[i] + len(nb)
+    return indptr, (np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64))
+
+
+def make_workload(n_graphs, rank=0, fixed_n=None, K=5, F=32):
+    rng = np.random.default_rng(0 + 7919 * rank)
+    sizes = np.full(n_graphs, fixed_n) if fixed_n else rng.choice(SIZES, size=n_graphs)
+    goff = np.zeros(n_graphs + 1, dtype=np.int64)
+    rps, cis = [np.zeros(1, dtype=np.int64)], []
+    noff = zoff = 0
+    for i, n in enumerate(sizes):
+        ip, ci = ba_csr(int(n), 1000 + i + 100003 * rank)
+        rps.append(ip[1:] + zoff)
+        cis.append(ci + noff)
+        noff += int(n); zoff += ci.size
+        goff[i + 1] = noff
+    rowptr = np.concatenate(rps).astype(np.int32)
+    colidx = np.concatenate(cis).astype(np.int32)
+    X = np.random.default_rng(1 + rank).normal(size=(noff, F)).astype(np.float32)
+    lim = np.sqrt(6.0 / (K * F + K * F))
+    W = np.random.default_rng(2).uniform(-lim, lim, size=(K, F, F))
+    b = np.zeros(F)
+    return dict(sizes=sizes, graph_off=goff.astype(np.int32), rowptr=rowptr, colidx=colidx, X=X, W=W, b=b, K=K, F=F)
+
+
+def algorithmic_bytes(w):
+    """4 n F_in + 4 n F_out + 4 (n+1) + 8 nnz per graph (fp32 values, int32 ids;
+    binary operator => the 4 B/nnz value stream is not read: 4 nnz; T_k stay on chip)."""
+    n = int(w["graph_off"][-1]); nnz = int(w["rowptr"][-1]); B = len(w["sizes"]); F = w["F"]
+    return 4 * n * F + 4 * n * F + 4 * (n + B) + 4 * nnz
+
+
+def algorithmic_flops(w):
+    n = int(w["graph_off"][-1]); nnz = int(w["rowptr"][-1]); F = w["F"]; K = w["K"]
+    return 2 * nnz * F * (K - 1) + 2 * n * K * F * F
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's per-graph fp64 path
+# --------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, seconds=10.0, threads=0, max_passes=1000):
+    """graph-steps/s of the reference's CPU path restated in C (fp64, one graph at a time as the
+    reference's eager call does, graphs spread over `threads` OpenMP threads; 0 = all)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    ws = [(w["W"], w["b"])]
+    X64 = w["X"].astype(np.float64)
+    c_oracle.stack_forward(w["graph_off"], w["rowptr"], w["colidx"], None, ws, [2], 0.2, X64, threads)  # warm
+    t0 = time.perf_counter(); passes = 0
+    while True:
+        c_oracle.stack_forward(w["graph_off"], w["rowptr"], w["colidx"], None, ws, [2], 0.2, X64, threads)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or passes >= max_passes:
+            break
+    cores = threads if threads > 0 else c_oracle.max_threads()
+    return len(w["sizes"]) * passes / dt, cores, passes, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = make_workload(args.graphs, 0, args.fixed_n)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    ws = [(w["W"], w["b"])]
+    X64 = w["X"].astype(np.float64)
+    cores = c_oracle.max_threads()
+    for _ in range(max(args.warmup, 1)):
+        c_oracle.stack_forward(w["graph_off"], w["rowptr"], w["colidx"], None, ws, [2], 0.2, X64, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.stack_forward(w["graph_off"], w["rowptr"], w["colidx"], None, ws, [2], 0.2, X64, 0)
+    dt = time.perf_counter() - t0
+    val = args.graphs * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, w),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d full passes over the %d-graph batch (oracle/cheb_oracle.c, fp64, one graph at a "
+                                   "time, OpenMP over graphs)" % (args.steps, args.graphs)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference hot path is TensorFlow+Spektral (not installable offline): timed arm is the oracle port",
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def workload_config(args, w):
+    return {"workload": "configs[1]: ChebConv K=%d forward, %d->%d, bias+leaky_relu, batch %d BA(m=2) graphs, n in %s, "
+                        "raw-adjacency operator" % (w["K"], w["F"], w["F"], args.graphs,
+                                                    "{%d}" % args.fixed_n if args.fixed_n else "{20..110 step 10}"),
+            "graphs_per_gpu": args.graphs, "nodes_per_gpu": int(w["graph_off"][-1]), "nnz_per_gpu": int(w["rowptr"][-1]),
+            "parallelism": "graph-instance sharding, no data-path collective",
+            "l2": "rotating over distinct input/output sets > 2x L2"}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from multihop_offload_b200 import ChebNet, GraphBatch, LayerSpec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = make_workload(args.graphs, rank, args.fixed_n)
+    net = ChebNet([LayerSpec(w["K"], w["F"], w["F"], 2, 0.2)], device=dev)
+    net.set_weights([(w["W"], w["b"])])
+    n_nodes = int(w["graph_off"][-1])
+    alg_bytes = algorithmic_bytes(w)
+    R = max(2, int(np.ceil(2.2 * L2_BYTES / alg_bytes)))
+    batches = [GraphBatch(w["graph_off"], w["rowptr"], w["colidx"], None, tile_rows=args.tile_rows, device=dev)
+               for _ in range(R)]
+    X0 = torch.from_numpy(w["X"]).to(dev)
+    Xs = [X0] + [torch.randn_like(X0) for _ in range(R - 1)]
+    Ys = [torch.empty((n_nodes, w["F"]), dtype=torch.float32, device=dev) for _ in range(R)]
+
+    def step(i):
+        j = i % R
+        net.forward(batches[j], Xs[j], out=Ys[j])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = net.ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = net.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers in, host buffers out, through the C-ABI host call
+    Xh = torch.from_numpy(w["X"]).pin_memory()
+    Yh = torch.empty((n_nodes, w["F"]), dtype=torch.float32).pin_memory()
+    goff_h = torch.from_numpy(w["graph_off"]).pin_memory()
+    rp_h = torch.from_numpy(w["rowptr"]).pin_memory()
+    ci_h = torch.from_numpy(w["colidx"]).pin_memory()
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        net.forward_host(goff_h.numpy(), rp_h.numpy(), ci_h.numpy(), None, Xh.numpy(), Yh.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        net.forward_host(goff_h.numpy(), rp_h.numpy(), ci_h.numpy(), None, Xh.numpy(), Yh.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(Xh.numel() * 4 + goff_h.numel() * 4 + rp_h.numel() * 4 + ci_h.numel() * 4)
+    d2h = int(Yh.numel() * 4)
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    value = world * args.graphs * args.steps / (ms * 1e-3)
+    e2e_val = world * args.graphs * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        per_launch_ms = ms / max(launches, 1)
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp32 storage/accumulate, 3xTF32 tensor-core products)", "data": "synthetic",
+            "config": workload_config(args, w),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "mho_cheb_forward_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "cheb_forward_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "tflops_algorithmic": algorithmic_flops(w) / (per_launch_ms * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, passes, dt = cpu_reference_rate(w, seconds=args.cpu_seconds, threads=1)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "%d passes over the same %d-graph batch in %.1f s (oracle/cheb_oracle.c: fp64, "
+                                             "one graph at a time like the reference's eager call, 1 thread)" % (passes, args.graphs, dt)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs", type=int, default=1024, help="graphs per GPU per step")
+    ap.add_argument("--fixed-n", type=int, default=None, help="all graphs of this size (e.g. 100)")
+    ap.add_argument("--tile-rows", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            pass  # each step is a full pass (~0.1 s with 8 threads); the driver picks K
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

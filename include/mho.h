@@ -1,0 +1,145 @@
+/*
+ * mho.h - C-ABI of libmho.so: the B200-native (sm_100a) batched ChebConv hot path of
+ * zhongyuanzhao/multihop-offload.
+ *
+ * The reference has no FFI: its seam is the Python call `self.model([x_in, a_in])`
+ * (src/gnn_offloading_agent.py:149, model built at :81-123 from spektral.layers.ChebConv) and
+ * the tape VJP `g.gradient(delay_mtx_ts, weights, output_gradients=...)` (:448), plus the
+ * optimizer replay (:156-169) that consumes the gradients.  Each entry point below names the
+ * reference interface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions: plain C, int return (0 = ok, <0 = mho_status), message via mho_last_error();
+ * all array arguments are caller-owned DEVICE pointers unless the name ends in _host; the
+ * callee never frees caller memory; every launch goes to the caller-supplied stream; no hidden
+ * synchronisation except in the *_host convenience calls (documented).  One context per
+ * (thread, GPU).  fp32 storage, fp32 accumulate, 3xTF32 split products on the tensor cores.
+ */
+#ifndef MHO_H_
+#define MHO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHO_VERSION 100
+
+typedef struct mho_ctx mho_ctx_t;
+typedef void* mho_stream_t; /* a cudaStream_t; NULL = the legacy default stream */
+
+typedef enum {
+    MHO_OK = 0,
+    MHO_ERR_INVALID = -1,      /* bad argument (NULL pointer, K<1, F>32, ...) */
+    MHO_ERR_TOO_LARGE = -2,    /* a graph/tile exceeds what one CTA can hold in shared memory */
+    MHO_ERR_CUDA = -3,         /* a CUDA runtime call failed; mho_last_error() has the string */
+    MHO_ERR_NO_DEVICE = -4,    /* no sm_100 device: there is NO CPU fallback by design */
+    MHO_ERR_NCCL = -5
+} mho_status;
+
+enum { MHO_ACT_NONE = 0, MHO_ACT_RELU = 1, MHO_ACT_LEAKY = 2 };
+enum { MHO_MAX_F = 32, MHO_MAX_K = 16, MHO_MAX_LAYERS = 16, MHO_MAX_TILE_ROWS = 512 };
+
+/*
+ * A batch of independent graphs, concatenated block-diagonally (the reference evaluates one
+ * graph per eager call, gnn_offloading_agent.py:144-150; a batch is many such calls at once).
+ * Operator = whatever the caller supplies; the reference feeds the raw binary adjacency of
+ * the extended line graph (:218), sorted row-major (spektral.utils.sp_matrix_to_sp_tensor,
+ * call site :148) - i.e. CSR.
+ */
+typedef struct {
+    int32_t n_graphs;
+    int32_t total_nodes;
+    int64_t total_nnz;
+    const int32_t* graph_off;  /* [n_graphs+1] node offset of each graph */
+    const int32_t* rowptr;     /* [total_nodes+1] offsets into colidx/vals (global) */
+    const int32_t* colidx;     /* [total_nnz] GLOBAL node ids (block-diagonal CSR) */
+    const float*   vals;       /* [total_nnz] or NULL => every stored entry is 1.0 */
+    /* transpose operator for the VJP; all three NULL => operator is symmetric (every graph the
+       reference produces is: undirected line graph), and the forward arrays are reused */
+    const int32_t* rowptr_t;
+    const int32_t* colidx_t;
+    const float*   vals_t;
+    /* tile plan (from mho_plan_tiles): tile t = graphs [tile_off[t], tile_off[t+1]) processed
+       by one CTA; NULL => one graph per tile */
+    const int32_t* tile_off;   /* [n_tiles+1] graph indices, device */
+    int32_t n_tiles;
+    int32_t max_tile_rows;     /* max over tiles of the node count (host-known) */
+    int32_t max_tile_nnz;      /* max over tiles of the nnz count (host-known) */
+} mho_batch_t;
+
+/* One ChebConv layer: Y = act(sum_k T_k(A) X W[k] + b), T_0=X, T_1=A X, T_k=2 A T_{k-1}-T_{k-2}
+ * (spektral.layers.ChebConv.call; K is the Spektral default 1 in the shipped model,
+ * gnn_offloading_agent.py:95-110).  W is [K, f_in, f_out] row-major = the Keras kernel layout
+ * stored in the checkpoints; b is [f_out] or NULL. */
+typedef struct {
+    int32_t K, f_in, f_out, act;
+    float slope;               /* leaky_relu negative slope (0.2 = tf.nn.leaky_relu default) */
+    const float* W;
+    const float* b;
+} mho_layer_t;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int mho_create(mho_ctx_t** ctx, int device);
+int mho_destroy(mho_ctx_t* ctx);
+const char* mho_last_error(void);
+int mho_version(void);
+/* number of kernels launched through this context so far (bench.py's gpu_launches claim) */
+int64_t mho_launch_count(const mho_ctx_t* ctx);
+
+/* ---- host-side planning helper (pure CPU, no CUDA): greedy packing of consecutive graphs
+ * into tiles of at most tile_rows nodes.  graph_off_host/rowptr_host are HOST copies.
+ * tile_off_host must have room for n_graphs+1 entries.  Graphs larger than tile_rows get a
+ * tile of their own (up to MHO_MAX_TILE_ROWS). */
+int mho_plan_tiles(const int32_t* graph_off_host, const int32_t* rowptr_host, int32_t n_graphs,
+                   int32_t tile_rows, int32_t* tile_off_host, int32_t* n_tiles,
+                   int32_t* max_tile_rows, int32_t* max_tile_nnz);
+
+/* ---- forward: replaces ACOAgent.predict -> self.model([x_in, a_in])
+ * (gnn_offloading_agent.py:144-150) for a whole batch.  X [total_nodes, layers[0].f_in],
+ * Y [total_nodes, layers[n-1].f_out], both row-major fp32.  `saved` (nullable) receives the
+ * inputs of layers 1..n-1 (the hidden activations) for the VJP: mho_saved_bytes() bytes. */
+int mho_cheb_forward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
+                     int32_t n_layers, const float* X, float* Y, void* saved, mho_stream_t stream);
+size_t mho_saved_bytes(const mho_batch_t* batch, const mho_layer_t* layers, int32_t n_layers);
+
+/* ---- backward: replaces g.gradient(delay_mtx_ts, model.trainable_weights, output_gradients)
+ * (gnn_offloading_agent.py:448) from the GNN output back to the weights.  dY is the gradient
+ * wrt Y (the caller has already pulled grad_dist through the queue head).  grads_per_graph
+ * [n_graphs, n_params] receives one flat gradient per graph instance in variable-creation order
+ * (kernel_0, bias_0, kernel_1, ...; the order the reference memorises them, :142,:450);
+ * grads_sum [n_params] (nullable) their deterministic sum (the buffer a data-parallel
+ * all-reduce ships).  dX nullable.  Requires a one-graph-per-tile batch (tile_off == NULL). */
+int mho_cheb_backward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
+                      int32_t n_layers, const float* X, const float* Y, const void* saved,
+                      const float* dY, float* grads_per_graph, float* grads_sum, float* dX,
+                      mho_stream_t stream);
+int64_t mho_param_count(const mho_layer_t* layers, int32_t n_layers);
+
+/* ---- optimizer: replaces ACOAgent.replay's loop of optimizer.apply_gradients
+ * (gnn_offloading_agent.py:156-169) with Keras Adam(clipnorm=1) (:114-121) and the
+ * max_norm(1.0, axis=0) constraints (:104-108): applies n_steps stored gradients
+ * SEQUENTIALLY in one launch.  params/m/v are flat fp32 [n_params] in the layout above;
+ * grads [n_steps, n_params]; step_count is the optimizer's iteration counter before the call. */
+typedef struct {
+    float lr, beta1, beta2, eps, clipnorm, max_norm; /* clipnorm<=0 / max_norm<=0 disable */
+    float decay_rate; int32_t decay_steps;           /* ExponentialDecay; decay_rate==1 => constant */
+} mho_adam_t;
+int mho_adam_replay(mho_ctx_t* ctx, const mho_layer_t* layers, int32_t n_layers,
+                    const mho_adam_t* cfg, float* params, float* m, float* v,
+                    const float* grads, int32_t n_steps, int64_t step_count, mho_stream_t stream);
+
+/* ---- host-buffer convenience (the reference-facing call: numpy in, numpy out, as
+ * ACOAgent.predict takes them).  All pointers are HOST memory (pinned for full speed); the
+ * call uploads the batch + X, runs mho_cheb_forward, downloads Y and synchronises `stream`.
+ * Weights inside `layers` are still DEVICE pointers (they live on the GPU across steps). */
+int mho_cheb_forward_host(mho_ctx_t* ctx, int32_t n_graphs, const int32_t* graph_off_host,
+                          const int32_t* rowptr_host, const int32_t* colidx_host,
+                          const float* vals_host, const mho_layer_t* layers, int32_t n_layers,
+                          const float* X_host, float* Y_host, mho_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHO_H_ */

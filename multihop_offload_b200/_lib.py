@@ -1,0 +1,117 @@
+"""ctypes binding of libmho.so (include/mho.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+MAX_F, MAX_K, MAX_LAYERS, MAX_TILE_ROWS = 32, 16, 16, 512
+
+
+class MhoError(RuntimeError):
+    pass
+
+
+class mho_batch_t(C.Structure):
+    _fields_ = [
+        ("n_graphs", C.c_int32), ("total_nodes", C.c_int32), ("total_nnz", C.c_int64),
+        ("graph_off", C.c_void_p), ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
+        ("rowptr_t", C.c_void_p), ("colidx_t", C.c_void_p), ("vals_t", C.c_void_p),
+        ("tile_off", C.c_void_p), ("n_tiles", C.c_int32), ("max_tile_rows", C.c_int32),
+        ("max_tile_nnz", C.c_int32),
+    ]
+
+
+class mho_layer_t(C.Structure):
+    _fields_ = [("K", C.c_int32), ("f_in", C.c_int32), ("f_out", C.c_int32), ("act", C.c_int32),
+                ("slope", C.c_float), ("W", C.c_void_p), ("b", C.c_void_p)]
+
+
+class mho_adam_t(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("clipnorm", C.c_float), ("max_norm", C.c_float), ("decay_rate", C.c_float),
+                ("decay_steps", C.c_int32)]
+
+
+# every symbol include/mho.h declares: (name, restype, argtypes)
+PROTOTYPES = [
+    ("mho_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    ("mho_destroy", C.c_int, [C.c_void_p]),
+    ("mho_last_error", C.c_char_p, []),
+    ("mho_version", C.c_int, []),
+    ("mho_launch_count", C.c_int64, [C.c_void_p]),
+    ("mho_plan_tiles", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("mho_cheb_forward", C.c_int, [C.c_void_p, C.POINTER(mho_batch_t), C.POINTER(mho_layer_t), C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mho_saved_bytes", C.c_size_t, [C.POINTER(mho_batch_t), C.POINTER(mho_layer_t), C.c_int32]),
+    ("mho_cheb_backward", C.c_int, [C.c_void_p, C.POINTER(mho_batch_t), C.POINTER(mho_layer_t), C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    ("mho_param_count", C.c_int64, [C.POINTER(mho_layer_t), C.c_int32]),
+    ("mho_adam_replay", C.c_int, [C.c_void_p, C.POINTER(mho_layer_t), C.c_int32, C.POINTER(mho_adam_t),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                  C.c_void_p]),
+    ("mho_cheb_forward_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(mho_layer_t), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+]
+
+
+def lib_path():
+    return os.environ.get("MHO_LIB", os.path.join(HERE, "libmho.so"))
+
+
+def load_library():
+    """dlopen libmho.so and type every entry point.  No fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MhoError("libmho.so not found at %s - build it with `python -m multihop_offload_b200.build` "
+                       "(or __graft_entry__.build()); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, res, args in PROTOTYPES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load_library().mho_last_error()
+        raise MhoError("%s failed (%d): %s" % (what or "libmho call", rc, (msg or b"").decode()))
+
+
+class Context:
+    """One mho_ctx_t per (process, GPU)."""
+    _cache = {}
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        check(self.lib.mho_create(C.byref(self.handle), int(device)), "mho_create")
+        self.device = int(device)
+
+    @classmethod
+    def get(cls, device=0):
+        device = int(device)
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    def launch_count(self):
+        return int(self.lib.mho_launch_count(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.mho_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

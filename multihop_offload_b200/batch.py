@@ -1,0 +1,153 @@
+"""GraphBatch: many independent graph instances concatenated block-diagonally (mho_batch_t).
+
+The reference converts one scipy adjacency per call (spektral.utils.sp_matrix_to_sp_tensor,
+call site src/gnn_offloading_agent.py:148) - coordinates sorted row-major, i.e. CSR.  Here the
+conversion happens once per batch on the host (numpy), the arrays then live in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _csr_parts(A):
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A)
+    if not A.has_sorted_indices:
+        A = A.sorted_indices()
+    return A.indptr, A.indices, A.data, A.shape[0]
+
+
+class GraphBatch:
+    """Host CSR arrays (+ device copies) of a block-diagonal batch and its tile plan."""
+
+    def __init__(self, graph_off, rowptr, colidx, vals=None, symmetric=True, tile_rows=128, device=None,
+                 transpose=None):
+        self.graph_off = np.ascontiguousarray(graph_off, dtype=np.int32)
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        self.colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        self.vals = None if vals is None else np.ascontiguousarray(vals, dtype=np.float32)
+        self.n_graphs = int(self.graph_off.size - 1)
+        self.total_nodes = int(self.graph_off[-1]) if self.graph_off.size else 0
+        self.total_nnz = int(self.rowptr[-1]) if self.rowptr.size else 0
+        self.symmetric = bool(symmetric)
+        self.transpose = transpose  # (rowptr_t, colidx_t, vals_t) host arrays when not symmetric
+        assert self.rowptr.size == self.total_nodes + 1 and self.colidx.size == self.total_nnz
+        self.tile_rows = int(tile_rows)
+        self._plan(self.tile_rows)
+        self.dev = {}
+        self.device = None
+        if device is not None:
+            self.to(device)
+
+    # ---- constructors -------------------------------------------------------------------
+    @classmethod
+    def from_scipy(cls, mats, binary=None, **kw):
+        """mats: list of scipy sparse operators, one per graph instance."""
+        g_off = np.zeros(len(mats) + 1, dtype=np.int64)
+        rps, cis, vas = [np.zeros(1, dtype=np.int64)], [], []
+        noff = zoff = 0
+        sym = True
+        for i, A in enumerate(mats):
+            indptr, indices, data, n = _csr_parts(A)
+            rps.append(indptr[1:].astype(np.int64) + zoff)
+            cis.append(indices.astype(np.int64) + noff)
+            vas.append(np.asarray(data, dtype=np.float64))
+            noff += n
+            zoff += indices.size
+            g_off[i + 1] = noff
+            if sym:
+                import scipy.sparse as sp
+                A2 = sp.csr_matrix(A)
+                sym = (abs(A2 - A2.T)).nnz == 0
+        rowptr = np.concatenate(rps)
+        colidx = np.concatenate(cis) if cis else np.zeros(0, dtype=np.int64)
+        vals = np.concatenate(vas) if vas else np.zeros(0)
+        if binary is None:
+            binary = bool(np.all(vals == 1.0))
+        transpose = None
+        if not sym:
+            import scipy.sparse as sp
+            Ablk = sp.csr_matrix((vals, colidx, rowptr), shape=(noff, noff)).T.tocsr()
+            Ablk.sort_indices()
+            transpose = (Ablk.indptr.astype(np.int32), Ablk.indices.astype(np.int32), Ablk.data.astype(np.float32))
+        return cls(g_off, rowptr, colidx, None if binary else vals, symmetric=sym, transpose=transpose, **kw)
+
+    # ---- tile plan ----------------------------------------------------------------------
+    def _plan(self, tile_rows):
+        lib = _lib.load_library()
+        tile_off = np.zeros(self.n_graphs + 1, dtype=np.int32)
+        nt, mr, mz = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(lib.mho_plan_tiles(self.graph_off.ctypes.data, self.rowptr.ctypes.data, self.n_graphs,
+                                      int(tile_rows), tile_off.ctypes.data, C.byref(nt), C.byref(mr), C.byref(mz)),
+                   "mho_plan_tiles")
+        self.n_tiles, self.max_tile_rows, self.max_tile_nnz = nt.value, mr.value, mz.value
+        self.tile_off = tile_off[: self.n_tiles + 1].copy()
+        # one-graph-per-tile statistics (the backward runs one graph per CTA)
+        if self.n_graphs:
+            sizes = np.diff(self.graph_off)
+            nnzs = self.rowptr[self.graph_off[1:]] - self.rowptr[self.graph_off[:-1]]
+            self.max_graph_rows, self.max_graph_nnz = int(sizes.max()), int(nnzs.max())
+        else:
+            self.max_graph_rows = self.max_graph_nnz = 0
+
+    # ---- device residency ---------------------------------------------------------------
+    def to(self, device):
+        import torch
+        device = torch.device(device)
+        self.device = device
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+
+        self.dev = dict(graph_off=up(self.graph_off), rowptr=up(self.rowptr), colidx=up(self.colidx),
+                        tile_off=up(self.tile_off))
+        if self.vals is not None:
+            self.dev["vals"] = up(self.vals)
+        if self.transpose is not None:
+            self.dev["rowptr_t"], self.dev["colidx_t"], self.dev["vals_t"] = (up(a) for a in self.transpose)
+        return self
+
+    def struct(self, per_graph_tiles=False):
+        """mho_batch_t over the device arrays.  per_graph_tiles=True => tile_off NULL (backward)."""
+        assert self.dev, "GraphBatch.to(device) first"
+        b = _lib.mho_batch_t()
+        b.n_graphs, b.total_nodes, b.total_nnz = self.n_graphs, self.total_nodes, self.total_nnz
+        b.graph_off = self.dev["graph_off"].data_ptr()
+        b.rowptr = self.dev["rowptr"].data_ptr()
+        b.colidx = self.dev["colidx"].data_ptr() if self.total_nnz else None
+        b.vals = self.dev["vals"].data_ptr() if "vals" in self.dev else None
+        if self.transpose is not None:
+            b.rowptr_t = self.dev["rowptr_t"].data_ptr()
+            b.colidx_t = self.dev["colidx_t"].data_ptr()
+            b.vals_t = self.dev["vals_t"].data_ptr() if "vals" in self.dev else None
+        if per_graph_tiles:
+            b.tile_off, b.n_tiles = None, self.n_graphs
+            b.max_tile_rows, b.max_tile_nnz = self.max_graph_rows, self.max_graph_nnz
+        else:
+            b.tile_off, b.n_tiles = self.dev["tile_off"].data_ptr(), self.n_tiles
+            b.max_tile_rows, b.max_tile_nnz = self.max_tile_rows, self.max_tile_nnz
+        return b
+
+    # ---- sharding across ranks (partition by graph, balanced by rows+nnz) ------
+    def shard(self, rank, world):
+        """Contiguous shard of graphs for `rank`, balanced on (nodes + nnz)."""
+        if world == 1:
+            return self
+        sizes = np.diff(self.graph_off).astype(np.int64)
+        nnzs = (self.rowptr[self.graph_off[1:]] - self.rowptr[self.graph_off[:-1]]).astype(np.int64)
+        cost = np.concatenate([[0], np.cumsum(32 * sizes + nnzs)])
+        bounds = [int(np.searchsorted(cost, cost[-1] * r / world, side="left")) for r in range(world + 1)]
+        bounds[0], bounds[-1] = 0, self.n_graphs
+        g0, g1 = bounds[rank], max(bounds[rank], bounds[rank + 1])
+        n0, n1 = int(self.graph_off[g0]), int(self.graph_off[g1])
+        z0, z1 = int(self.rowptr[n0]), int(self.rowptr[n1])
+        sub = GraphBatch(self.graph_off[g0:g1 + 1] - n0, self.rowptr[n0:n1 + 1] - z0, self.colidx[z0:z1] - n0,
+                         None if self.vals is None else self.vals[z0:z1], symmetric=self.symmetric,
+                         tile_rows=self.tile_rows)
+        sub.node_range = (n0, n1)
+        sub.graph_range = (g0, g1)
+        return sub

@@ -1,0 +1,243 @@
+// C-ABI glue of libmho.so: context, argument validation, tile planning, launch wrappers.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "mho_common.cuh"
+#include "mho_internal.h"
+
+static thread_local char g_err[512] = "";
+
+void mho_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            mho_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return MHO_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+extern "C" const char* mho_last_error(void) { return g_err; }
+extern "C" int mho_version(void) { return MHO_VERSION; }
+
+extern "C" int mho_create(mho_ctx_t** out, int device) {
+    if (!out) { mho_set_error("mho_create: ctx is NULL"); return MHO_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        mho_set_error("mho_create: no CUDA device visible; libmho has no CPU fallback");
+        return MHO_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { mho_set_error("mho_create: device %d out of range [0,%d)", device, n); return MHO_ERR_INVALID; }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        mho_set_error("mho_create: device %d is sm_%d%d; libmho is built for sm_100a only", device, prop.major, prop.minor);
+        return MHO_ERR_NO_DEVICE;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    mho_ctx* c = new mho_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = c;
+    return MHO_OK;
+}
+
+extern "C" int mho_destroy(mho_ctx_t* c) {
+    if (!c) return MHO_OK;
+    cudaSetDevice(c->device);
+    for (auto& s : c->scratch) if (s.ptr) cudaFree(s.ptr);
+    delete c;
+    return MHO_OK;
+}
+
+extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
+
+// grow-only device scratch slots (used by the *_host convenience calls and the backward reducer)
+void* mho_scratch(mho_ctx* c, int slot, size_t bytes) {
+    if ((int)c->scratch.size() <= slot) c->scratch.resize(slot + 1);
+    auto& s = c->scratch[slot];
+    if (s.bytes < bytes) {
+        if (s.ptr) cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&s.ptr, want) != cudaSuccess) { s.ptr = nullptr; return nullptr; }
+        s.bytes = want;
+    }
+    return s.ptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int mho_plan_tiles(const int32_t* goff, const int32_t* rowptr, int32_t n_graphs, int32_t tile_rows,
+                              int32_t* tile_off, int32_t* n_tiles, int32_t* max_rows, int32_t* max_nnz) {
+    if (!goff || !rowptr || !tile_off || !n_tiles || !max_rows || !max_nnz || n_graphs < 0 || tile_rows < 1) {
+        mho_set_error("mho_plan_tiles: invalid argument");
+        return MHO_ERR_INVALID;
+    }
+    int nt = 0, mr = 0, mz = 0;
+    int g = 0;
+    tile_off[0] = 0;
+    while (g < n_graphs) {
+        int start = g;
+        int rows = goff[g + 1] - goff[g];
+        if (rows > MHO_MAX_TILE_ROWS) {
+            mho_set_error("mho_plan_tiles: graph %d has %d nodes; one CTA holds at most %d", g, rows, MHO_MAX_TILE_ROWS);
+            return MHO_ERR_TOO_LARGE;
+        }
+        ++g;
+        while (g < n_graphs && (goff[g + 1] - goff[start]) <= tile_rows) ++g;
+        rows = goff[g] - goff[start];
+        int nnz = rowptr[goff[g]] - rowptr[goff[start]];
+        mr = rows > mr ? rows : mr;
+        mz = nnz > mz ? nnz : mz;
+        tile_off[++nt] = g;
+    }
+    *n_tiles = nt;
+    *max_rows = mr;
+    *max_nnz = mz;
+    return MHO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int validate_layers(const mho_layer_t* layers, int n_layers, const char* who) {
+    if (!layers || n_layers < 1 || n_layers > MHO_MAX_LAYERS) { mho_set_error("%s: n_layers=%d not in [1,%d]", who, n_layers, MHO_MAX_LAYERS); return MHO_ERR_INVALID; }
+    for (int l = 0; l < n_layers; ++l) {
+        const mho_layer_t& L = layers[l];
+        if (L.K < 1 || L.K > MHO_MAX_K || L.f_in < 1 || L.f_in > MHO_MAX_F || L.f_out < 1 || L.f_out > MHO_MAX_F || !L.W ||
+            L.act < 0 || L.act > 2) {
+            mho_set_error("%s: layer %d invalid (K=%d f_in=%d f_out=%d act=%d W=%p); limits K<=%d F<=%d", who, l, L.K, L.f_in,
+                          L.f_out, L.act, (const void*)L.W, MHO_MAX_K, MHO_MAX_F);
+            return MHO_ERR_INVALID;
+        }
+        if (l > 0 && layers[l - 1].f_out != L.f_in) { mho_set_error("%s: layer %d f_in=%d != previous f_out=%d", who, l, L.f_in, layers[l - 1].f_out); return MHO_ERR_INVALID; }
+    }
+    return MHO_OK;
+}
+
+static int validate_batch(const mho_batch_t* b, const char* who) {
+    if (!b || b->n_graphs < 0 || !b->graph_off || !b->rowptr || (b->total_nnz > 0 && !b->colidx)) { mho_set_error("%s: invalid batch", who); return MHO_ERR_INVALID; }
+    if (b->max_tile_rows < 1 && b->n_graphs > 0) { mho_set_error("%s: batch.max_tile_rows must be set (mho_plan_tiles)", who); return MHO_ERR_INVALID; }
+    return MHO_OK;
+}
+
+void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, LayerDev* out) {
+    long long poff = 0, soff = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        out[l].K = layers[l].K; out[l].f_in = layers[l].f_in; out[l].f_out = layers[l].f_out;
+        out[l].act = layers[l].act; out[l].slope = layers[l].slope;
+        out[l].W = layers[l].W; out[l].b = layers[l].b;
+        out[l].param_off = poff;
+        poff += (long long)layers[l].K * layers[l].f_in * layers[l].f_out + layers[l].f_out;
+        out[l].saved_off = 0;
+        if (l >= 1) { out[l].saved_off = soff; soff += (long long)total_nodes * layers[l].f_in; }
+    }
+}
+
+extern "C" int64_t mho_param_count(const mho_layer_t* layers, int32_t n_layers) {
+    if (!layers) return 0;
+    int64_t p = 0;
+    for (int l = 0; l < n_layers; ++l) p += (int64_t)layers[l].K * layers[l].f_in * layers[l].f_out + layers[l].f_out;
+    return p;
+}
+
+extern "C" size_t mho_saved_bytes(const mho_batch_t* b, const mho_layer_t* layers, int32_t n_layers) {
+    if (!b || !layers) return 0;
+    size_t s = 0;
+    for (int l = 1; l < n_layers; ++l) s += (size_t)b->total_nodes * layers[l].f_in * sizeof(float);
+    return s;
+}
+
+extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_layer_t* layers, int32_t n_layers,
+                                const float* X, float* Y, void* saved, mho_stream_t stream) {
+    if (!c) { mho_set_error("mho_cheb_forward: ctx is NULL"); return MHO_ERR_INVALID; }
+    int rc = validate_batch(b, "mho_cheb_forward");
+    if (rc) return rc;
+    rc = validate_layers(layers, n_layers, "mho_cheb_forward");
+    if (rc) return rc;
+    if (b->n_graphs == 0 || b->total_nodes == 0) return MHO_OK;  // empty batch: nothing to do
+    if (!X || !Y) { mho_set_error("mho_cheb_forward: X/Y is NULL"); return MHO_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.b.graph_off = b->graph_off; p.b.rowptr = b->rowptr; p.b.colidx = b->colidx; p.b.vals = b->vals;
+    p.b.tile_off = b->tile_off; p.b.n_graphs = b->n_graphs;
+    p.b.n_tiles = b->tile_off ? b->n_tiles : b->n_graphs;
+    p.n_layers = n_layers;
+    mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);
+    p.X = X; p.Y = Y; p.saved = (float*)saved; p.total_nodes = b->total_nodes;
+    bool too_large = false;
+    cudaError_t e = cheb_forward_launch(p, b->max_tile_rows, b->max_tile_nnz, c->num_sms, c->max_smem_optin,
+                                        (cudaStream_t)stream, &too_large);
+    if (too_large) {
+        mho_set_error("mho_cheb_forward: tile of %d rows / K up to %d does not fit in %d B of shared memory", b->max_tile_rows,
+                      MHO_MAX_K, c->max_smem_optin);
+        return MHO_ERR_TOO_LARGE;
+    }
+    if (e != cudaSuccess) { mho_set_error("cheb_forward launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    return MHO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer convenience: numpy in / numpy out, like ACOAgent.predict (gnn_offloading_agent.py:144-150)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
+                                     const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
+                                     int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream) {
+    if (!c || !goff_h || !rowptr_h || !X_h || !Y_h || n_graphs < 0) { mho_set_error("mho_cheb_forward_host: invalid argument"); return MHO_ERR_INVALID; }
+    int rc = validate_layers(layers, n_layers, "mho_cheb_forward_host");
+    if (rc) return rc;
+    if (n_graphs == 0) return MHO_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total_nodes = goff_h[n_graphs];
+    const int64_t nnz = rowptr_h[total_nodes];
+    if (total_nodes == 0) return MHO_OK;
+    std::vector<int32_t> tile_off((size_t)n_graphs + 1);
+    int32_t n_tiles = 0, mr = 0, mz = 0;
+    rc = mho_plan_tiles(goff_h, rowptr_h, n_graphs, 128, tile_off.data(), &n_tiles, &mr, &mz);
+    if (rc) return rc;
+    const int f_in = layers[0].f_in, f_out = layers[n_layers - 1].f_out;
+    const size_t b_goff = (size_t)(n_graphs + 1) * 4, b_rp = (size_t)(total_nodes + 1) * 4, b_ci = (size_t)nnz * 4;
+    const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_to = (size_t)(n_tiles + 1) * 4;
+    const size_t b_x = (size_t)total_nodes * f_in * 4, b_y = (size_t)total_nodes * f_out * 4;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total = al(b_goff) + al(b_rp) + al(b_ci) + al(b_va) + al(b_to) + al(b_x) + al(b_y);
+    char* base = (char*)mho_scratch(c, 0, total);
+    if (!base) { mho_set_error("mho_cheb_forward_host: cudaMalloc of %zu B failed", total); return MHO_ERR_CUDA; }
+    char* q = base;
+    int32_t* d_goff = (int32_t*)q; q += al(b_goff);
+    int32_t* d_rp = (int32_t*)q; q += al(b_rp);
+    int32_t* d_ci = (int32_t*)q; q += al(b_ci);
+    float* d_va = vals_h ? (float*)q : nullptr; q += al(b_va);
+    int32_t* d_to = (int32_t*)q; q += al(b_to);
+    float* d_x = (float*)q; q += al(b_x);
+    float* d_y = (float*)q;
+    CUDA_TRY(cudaMemcpyAsync(d_goff, goff_h, b_goff, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_rp, rowptr_h, b_rp, cudaMemcpyHostToDevice, st));
+    if (nnz) CUDA_TRY(cudaMemcpyAsync(d_ci, colidx_h, b_ci, cudaMemcpyHostToDevice, st));
+    if (vals_h && nnz) CUDA_TRY(cudaMemcpyAsync(d_va, vals_h, b_va, cudaMemcpyHostToDevice, st));
+    // tile_off lives in a std::vector that dies at return: stage it synchronously-safe via a pageable copy
+    CUDA_TRY(cudaMemcpyAsync(d_to, tile_off.data(), b_to, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_x, X_h, b_x, cudaMemcpyHostToDevice, st));
+    mho_batch_t b;
+    memset(&b, 0, sizeof(b));
+    b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
+    b.graph_off = d_goff; b.rowptr = d_rp; b.colidx = d_ci; b.vals = d_va;
+    b.tile_off = d_to; b.n_tiles = n_tiles; b.max_tile_rows = mr; b.max_tile_nnz = mz;
+    rc = mho_cheb_forward(c, &b, layers, n_layers, d_x, d_y, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Y_h, d_y, b_y, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MHO_OK;
+}

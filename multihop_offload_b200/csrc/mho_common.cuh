@@ -1,0 +1,117 @@
+// Shared device helpers for libmho (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mho.h"
+
+#define MHO_THREADS 256
+#define MHO_NWARPS (MHO_THREADS / 32)
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tile layout: [rows][32] fp32, one row = 128 B, 16-byte chunks XOR-swizzled with
+// (row & 7).  This is the canonical "K-major, SWIZZLE_128B" layout: conflict-free for the
+// row gathers of the sparse recurrence (a warp reads one row = 32 distinct banks), conflict-free
+// for ldmatrix (8 rows x 16 B land in 8 distinct bank groups), writable by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B and directly describable as a tcgen05 smem operand.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t col) {
+    return (row << 7) | ((((col >> 2) ^ (row & 7u)) << 4)) | ((col & 3u) << 2);
+}
+// row part of the offset with the swizzle key folded in: off(row, col) = swz_row(row) ^ lane_key(col)
+__device__ __forceinline__ uint32_t swz_row(uint32_t row) { return (row << 7) | ((row & 7u) << 4); }
+__device__ __forceinline__ uint32_t swz_key(uint32_t col) { return ((col >> 2) << 4) | ((col & 3u) << 2); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// ---------------------------------------------------------------------------------------------
+// 3xTF32: a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulate (error ~2^-21 per product)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float apply_act(float z, int act, float slope) {
+    if (act == MHO_ACT_RELU) return fmaxf(z, 0.f);
+    if (act == MHO_ACT_LEAKY) return z > 0.f ? z : slope * z;
+    return z;
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+    // act'(z) expressed with the OUTPUT y: for relu and leaky (slope>0) y>0 <=> z>0 (TF uses strict >)
+    if (act == MHO_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == MHO_ACT_LEAKY) return y > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+__host__ __device__ __forceinline__ int pad8(int x) { return (x + 7) & ~7; }
+__host__ __device__ __forceinline__ int pad16(int x) { return (x + 15) & ~15; }
+
+// Device-side view of one layer (pointers are device pointers)
+struct LayerDev {
+    int K, f_in, f_out, act;
+    float slope;
+    const float* W;
+    const float* b;
+    long long param_off;  // offset of this layer's kernel in the flat parameter vector
+    long long saved_off;  // element offset of this layer's INPUT inside `saved` (layers >= 1)
+};
+
+struct BatchDev {
+    const int32_t* graph_off;
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const float* vals;
+    const int32_t* tile_off;
+    int n_tiles;
+    int n_graphs;
+};
+
+struct FwdParams {
+    BatchDev b;
+    int n_layers;
+    LayerDev layers[MHO_MAX_LAYERS];
+    const float* X;
+    float* Y;
+    float* saved;     // nullable
+    int rows_cap;     // multiple of 16, >= max tile rows
+    int nnz_cap;      // staged nnz capacity (multiple of 4); 0 => read CSR from global memory
+    int w_rows_cap;   // rows (of 128 B) of one W image = max_l K_l * pad8(f_out_l)
+    int total_nodes;
+};

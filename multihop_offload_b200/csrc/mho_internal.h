@@ -1,0 +1,29 @@
+// Internal (non-ABI) declarations shared by the libmho translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/mho.h"
+
+struct mho_scratch_slot {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct mho_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+    std::vector<mho_scratch_slot> scratch;
+};
+
+void mho_set_error(const char* fmt, ...);
+void* mho_scratch(mho_ctx* c, int slot, size_t bytes);
+
+struct LayerDev;
+struct FwdParams;
+void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, LayerDev* out);
+cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
+                                cudaStream_t st, bool* too_large);

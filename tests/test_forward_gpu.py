@@ -1,0 +1,173 @@
+"""GPU parity: libmho forward (through the C-ABI) vs the fp64 oracle / committed goldens.
+
+Tolerance (north_star): 1e-5 relative, measured per graph as |y - y_ref|_inf / |y_ref|_inf.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import chebnet_oracle as O
+from helpers import oracle_batch_forward, random_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _net(specs, weights):
+    from multihop_offload_b200 import ChebNet
+    net = ChebNet(specs, device="cuda:0")
+    net.set_weights(weights)
+    return net
+
+
+def _run(torch, net, mats, X, tile_rows=128, binary=None):
+    from multihop_offload_b200 import GraphBatch
+    batch = GraphBatch.from_scipy(mats, tile_rows=tile_rows, binary=binary, device="cuda:0")
+    Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+    Y = net.forward(batch, Xd)
+    torch.cuda.synchronize()
+    return Y.cpu().numpy(), batch
+
+
+def test_golden_layer_k5_f32(torch_cuda, golden_dir):
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    z = np.load(os.path.join(golden_dir, "layer_K5_F32.npz"))
+    net = _net([LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)], [(z["W"], z["b"])])
+    for tile_rows in (128, 64, 256, 512):
+        batch = GraphBatch(z["graph_off"], z["rowptr"], z["colidx"], None, tile_rows=tile_rows, device="cuda:0")
+        Y = net.forward(batch, torch_cuda.from_numpy(z["X"].astype(np.float32)).cuda()).cpu().numpy()
+        err = rel_err(Y, z["Y"], z["graph_off"])
+        assert err < TOL, (tile_rows, err)
+
+
+def test_golden_rollout_cases_shipped_checkpoint(torch_cuda, golden_dir):
+    from multihop_offload_b200 import reference_stack
+    for tag, key, K in (("BAT800", "lam", 1), ("K3", "lam_K3", 3)):
+        w = np.load(os.path.join(golden_dir, "weights_%s.npz" % tag))
+        ws = [(w["W%d" % i], w["b%d" % i]) for i in range(5)]
+        net = _net(reference_stack(K=K), ws)
+        for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz"))):
+            z = np.load(f)
+            n = z["X"].shape[0]
+            A = sp.csr_matrix((z["vals"], z["colidx"], z["rowptr"]), shape=(n, n))
+            Y, _ = _run(torch_cuda, net, [A], z["X"], tile_rows=128)
+            err = rel_err(Y, z[key])
+            assert err < TOL, (tag, os.path.basename(f), err)
+            assert (Y >= 0).all()
+
+
+def test_random_batches_vs_oracle(torch_cuda):
+    from multihop_offload_b200 import LayerSpec, reference_stack
+    rng = np.random.default_rng(42)
+    configs = [
+        ([LayerSpec(5, 32, 32)], "raw-adj"),
+        ([LayerSpec(1, 32, 32)], "raw-adj"),
+        ([LayerSpec(2, 32, 32, O.ACT_RELU)], "raw-adj"),
+        ([LayerSpec(10, 32, 32)], "cheb-lap"),
+        ([LayerSpec(3, 4, 32), LayerSpec(3, 32, 1, O.ACT_RELU)], "raw-adj"),
+        ([LayerSpec(4, 7, 13), LayerSpec(2, 13, 20, O.ACT_NONE), LayerSpec(3, 20, 5, O.ACT_RELU)], "cheb-lap"),
+        (reference_stack(K=5), "cheb-lap"),
+    ]
+    for specs, op in configs:
+        sizes = rng.choice([20, 30, 40, 50, 60, 70, 80, 90, 100, 110], size=37)
+        mats = O.make_batch(sizes, seed0=int(rng.integers(1 << 20)), operator=op)
+        X = rng.normal(size=(int(sizes.sum()), specs[0].f_in))
+        ws = random_weights(specs, rng, scale=1.0 if op == "cheb-lap" else 0.5)
+        net = _net(specs, ws)
+        Y, batch = _run(torch_cuda, net, mats, X)
+        ref = oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2)
+        err = rel_err(Y, ref, batch.graph_off)
+        assert err < TOL, ([(s.K, s.f_in, s.f_out) for s in specs], op, err)
+
+
+def test_edge_cases(torch_cuda):
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    rng = np.random.default_rng(7)
+    specs = [LayerSpec(4, 32, 32)]
+    ws = random_weights(specs, rng, 0.5)
+    net = _net(specs, ws)
+    # empty batch
+    b0 = GraphBatch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), device="cuda:0")
+    Y0 = net.forward(b0, torch_cuda.empty((0, 32), dtype=torch_cuda.float32, device="cuda"))
+    assert Y0.shape == (0, 32)
+    # ragged: single-node graph without edges, empty rows, a 2-node graph, the largest supported graphs
+    mats = [sp.csr_matrix((1, 1)), sp.csr_matrix(np.array([[0., 1.], [1., 0.]])), O.ba_adjacency(3, 2, 1),
+            O.ba_adjacency(300, 2, 2), O.ba_adjacency(512, 2, 3), sp.csr_matrix((5, 5)), O.ba_adjacency(17, 2, 4)]
+    X = rng.normal(size=(sum(m.shape[0] for m in mats), 32))
+    for tr in (128, 512):
+        Y, batch = _run(torch_cuda, net, mats, X, tile_rows=tr)
+        ref = oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2)
+        assert rel_err(Y, ref, batch.graph_off) < TOL
+    # dense-ish hub graph whose CSR slice cannot be staged next to the tiles (falls back to L1/L2 reads)
+    hub = sp.random(500, 500, 0.2, random_state=1, format="csr")
+    hub.data[:] = rng.normal(size=hub.nnz) * 0.05
+    Xh = rng.normal(size=(500, 32))
+    Y, batch = _run(torch_cuda, net, [hub], Xh, tile_rows=512, binary=False)
+    assert rel_err(Y, oracle_batch_forward([hub], Xh, ws, [s.act for s in specs], 0.2)) < TOL
+
+
+def test_non_symmetric_weighted_operator(torch_cuda):
+    from multihop_offload_b200 import LayerSpec
+    rng = np.random.default_rng(9)
+    specs = [LayerSpec(5, 32, 32), LayerSpec(3, 32, 8, O.ACT_RELU)]
+    ws = random_weights(specs, rng, 0.7)
+    mats = []
+    for i in range(20):
+        n = int(rng.integers(5, 120))
+        A = sp.random(n, n, min(1.0, 6.0 / n), random_state=i, format="csr")
+        A.data[:] = rng.uniform(-0.3, 0.3, size=A.nnz)
+        mats.append(A)
+    X = rng.normal(size=(sum(m.shape[0] for m in mats), 32))
+    Y, batch = _run(torch_cuda, _net(specs, ws), mats, X, binary=False)
+    ref = oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2)
+    assert rel_err(Y, ref, batch.graph_off) < TOL
+
+
+def test_host_buffer_api(torch_cuda, golden_dir):
+    from multihop_offload_b200 import LayerSpec
+    z = np.load(os.path.join(golden_dir, "layer_K5_F32.npz"))
+    net = _net([LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)], [(z["W"], z["b"])])
+    Y = net.forward_host(z["graph_off"], z["rowptr"], z["colidx"], None, z["X"])
+    assert rel_err(Y, z["Y"], z["graph_off"]) < TOL
+
+
+def test_full_size_linearity_property(torch_cuda):
+    """BASELINE config 2 size (1024 graphs): with act=none the layer is linear in X, and
+    permuting the graph order permutes the output blocks - size-independent properties."""
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    rng = np.random.default_rng(0)
+    sizes = rng.choice(np.arange(20, 111, 10), size=1024)
+    mats = O.make_batch(sizes, seed0=1000)
+    specs = [LayerSpec(5, 32, 32, O.ACT_NONE)]
+    ws = random_weights(specs, rng, 0.3, bias=0.0)
+    net = _net(specs, ws)
+    batch = GraphBatch.from_scipy(mats, device="cuda:0")
+    n = batch.total_nodes
+    X1 = torch_cuda.randn(n, 32, device="cuda"); X2 = torch_cuda.randn(n, 32, device="cuda")
+    Y1 = net.forward(batch, X1); Y2 = net.forward(batch, X2)
+    Y12 = net.forward(batch, (2.0 * X1 - 0.5 * X2).contiguous())
+    scale = Y12.abs().max().item()
+    assert (Y12 - (2.0 * Y1 - 0.5 * Y2)).abs().max().item() <= 2e-5 * scale
+    # graph-order permutation
+    perm = rng.permutation(len(mats))
+    batch_p = GraphBatch.from_scipy([mats[i] for i in perm], device="cuda:0")
+    off = batch.graph_off
+    idx = np.concatenate([np.arange(off[i], off[i + 1]) for i in perm])
+    Yp = net.forward(batch_p, X1[torch_cuda.from_numpy(idx).cuda()].contiguous())
+    assert torch_cuda.equal(Yp, Y1[torch_cuda.from_numpy(idx).cuda()])
+    # and a sample of graphs against the oracle at full batch size
+    Xh = X1.cpu().numpy().astype(np.float64)
+    for gi in rng.choice(len(mats), size=16, replace=False):
+        a, b = off[gi], off[gi + 1]
+        ref = O.cheb_stack_forward(mats[gi], Xh[a:b], ws, [O.ACT_NONE])
+        assert rel_err(Y1[a:b].cpu().numpy(), ref) < TOL
