@@ -120,14 +120,16 @@ int64_t mho_param_count(const mho_layer_t* layers, int32_t n_layers);
 /* ---- optimizer: replaces ACOAgent.replay's loop of optimizer.apply_gradients
  * (gnn_offloading_agent.py:156-169) with Keras Adam(clipnorm=1) (:114-121) and the
  * max_norm(1.0, axis=0) constraints (:104-108): applies n_steps stored gradients
- * SEQUENTIALLY in one launch.  params/m/v are flat fp32 [n_params] in the layout above;
- * grads [n_steps, n_params]; step_count is the optimizer's iteration counter before the call. */
+ * SEQUENTIALLY in one launch.  The reference trains in fp64, so the master weights and the
+ * moments are fp64 device buffers [n_params] in the flat layout above (lr=1e-6 updates would
+ * drown in fp32); params_f32 receives the fp32 copy the forward/backward kernels read.
+ * grads [n_steps, n_params] fp32; step_count is the optimizer's iteration counter before the call. */
 typedef struct {
-    float lr, beta1, beta2, eps, clipnorm, max_norm; /* clipnorm<=0 / max_norm<=0 disable */
-    float decay_rate; int32_t decay_steps;           /* ExponentialDecay; decay_rate==1 => constant */
+    double lr, beta1, beta2, eps, clipnorm, max_norm; /* clipnorm<=0 / max_norm<=0 disable */
+    double decay_rate; int32_t decay_steps;           /* ExponentialDecay; decay_rate==1 => constant */
 } mho_adam_t;
 int mho_adam_replay(mho_ctx_t* ctx, const mho_layer_t* layers, int32_t n_layers,
-                    const mho_adam_t* cfg, float* params, float* m, float* v,
+                    const mho_adam_t* cfg, double* params, double* m, double* v, float* params_f32,
                     const float* grads, int32_t n_steps, int64_t step_count, mho_stream_t stream);
 
 /* ---- host-buffer convenience (the reference-facing call: numpy in, numpy out, as

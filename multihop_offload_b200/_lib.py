@@ -31,8 +31,8 @@ class mho_layer_t(C.Structure):
 
 
 class mho_adam_t(C.Structure):
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("clipnorm", C.c_float), ("max_norm", C.c_float), ("decay_rate", C.c_float),
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("clipnorm", C.c_double), ("max_norm", C.c_double), ("decay_rate", C.c_double),
                 ("decay_steps", C.c_int32)]
 
 
@@ -53,8 +53,8 @@ PROTOTYPES = [
                                     C.c_void_p, C.c_void_p]),
     ("mho_param_count", C.c_int64, [C.POINTER(mho_layer_t), C.c_int32]),
     ("mho_adam_replay", C.c_int, [C.c_void_p, C.POINTER(mho_layer_t), C.c_int32, C.POINTER(mho_adam_t),
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
-                                  C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int64, C.c_void_p]),
     ("mho_cheb_forward_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(mho_layer_t), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]

@@ -40,6 +40,7 @@ class GraphBatch:
         self._plan(self.tile_rows)
         self.dev = {}
         self.device = None
+        self._struct_cache = {}
         if device is not None:
             self.to(device)
 
@@ -99,6 +100,7 @@ class GraphBatch:
         import torch
         device = torch.device(device)
         self.device = device
+        self._struct_cache = {}
 
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
@@ -110,6 +112,16 @@ class GraphBatch:
         if self.transpose is not None:
             self.dev["rowptr_t"], self.dev["colidx_t"], self.dev["vals_t"] = (up(a) for a in self.transpose)
         return self
+
+    def struct_ref(self, per_graph_tiles=False):
+        """Cached ctypes byref of the mho_batch_t (device arrays never move after .to())."""
+        key = bool(per_graph_tiles)
+        c = self._struct_cache.get(key)
+        if c is None:
+            st = self.struct(per_graph_tiles=key)
+            c = (st, C.byref(st))
+            self._struct_cache[key] = c
+        return c[1]
 
     def struct(self, per_graph_tiles=False):
         """mho_batch_t over the device arrays.  per_graph_tiles=True => tile_off NULL (backward)."""

@@ -96,7 +96,11 @@ class ChebNet:
         return out
 
     def layer_structs(self, params=None):
-        p = self.params if params is None else params
+        if params is None:
+            if getattr(self, "_layers_cache", None) is None:
+                self._layers_cache = self.layer_structs(self.params)  # params buffer is never reallocated
+            return self._layers_cache
+        p = params
         base = p.data_ptr()
         arr = (_lib.mho_layer_t * len(self.specs))()
         for i, (s, (ow, ob)) in enumerate(zip(self.specs, self._offsets)):
@@ -117,15 +121,15 @@ class ChebNet:
         """X: float32 device tensor [total_nodes, f_in].  Returns Y (and the saved activations)."""
         import torch
         assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()
-        assert X.shape == (batch.total_nodes, self.specs[0].f_in), X.shape
+        assert X.shape[0] == batch.total_nodes and X.shape[1] == self.specs[0].f_in, X.shape
         Y = out if out is not None else torch.empty((batch.total_nodes, self.specs[-1].f_out), dtype=torch.float32,
                                                     device=self.device)
         saved = torch.empty(max(self.saved_floats(batch), 1), dtype=torch.float32, device=self.device) if save else None
-        b = batch.struct(per_graph_tiles=per_graph_tiles)
-        layers = self.layer_structs()
-        rc = self.ctx.lib.mho_cheb_forward(self.ctx.handle, C.byref(b), layers, len(self.specs), X.data_ptr(),
-                                           Y.data_ptr(), saved.data_ptr() if save else None, self._stream())
-        _lib.check(rc, "mho_cheb_forward")
+        rc = self.ctx.lib.mho_cheb_forward(self.ctx.handle, batch.struct_ref(per_graph_tiles), self.layer_structs(),
+                                           len(self.specs), X.data_ptr(), Y.data_ptr(),
+                                           saved.data_ptr() if save else None, self._stream())
+        if rc:
+            _lib.check(rc, "mho_cheb_forward")
         return (Y, saved) if save else Y
 
     def backward(self, batch, X, Y, saved, dY, need_dx=False, need_sum=True):

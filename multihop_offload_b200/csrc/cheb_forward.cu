@@ -88,7 +88,7 @@ __device__ __forceinline__ void mma_tile(float (&acc)[4][4], uint32_t T_addr, in
 // One step of the recurrence for the rows owned by this warp:
 //   first step : Tdst[r] = sum_j A[r,j] Tsrc[j]
 //   later steps: Tdst[r] = 2 sum_j A[r,j] Tsrc[j] - Tdst[r]      (T_{k+1} overwrites T_{k-1})
-// lane = feature column; every gather is one 128 B wavefront.
+// lane = feature column; every gather is one 128 B wavefront (gather_row in mho_common.cuh).
 // -------------------------------------------------------------------------------------------
 template <bool HAS_VALS, bool STAGED>
 __device__ __forceinline__ void spmm_step(uint32_t Tsrc, uint32_t Tdst, bool first, int rows, const int* rp_s,
@@ -97,49 +97,8 @@ __device__ __forceinline__ void spmm_step(uint32_t Tsrc, uint32_t Tdst, bool fir
                                           bool lane_on) {
     const uint32_t key = swz_key((uint32_t)lane);
     for (int r = warp; r < rows; r += MHO_NWARPS) {
-        const int e0 = rp_s[r], e1 = rp_s[r + 1];
-        float s0 = 0.f, s1 = 0.f;
         if (lane_on) {
-            int e = e0;
-            if (STAGED) {
-                // head (unaligned), body (LDS.128 of 4 pre-swizzled offsets), tail
-                for (; (e & 3) && e < e1; ++e) {
-                    uint32_t p;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p) : "r"(pre_a + e * 4));
-                    const float t = lds_f32(Tsrc + (p ^ key));
-                    s0 = HAS_VALS ? fmaf(lds_f32(val_a + e * 4), t, s0) : s0 + t;
-                }
-                for (; e + 4 <= e1; e += 4) {
-                    const uint4 p = lds_u128(pre_a + e * 4);
-                    const float t0 = lds_f32(Tsrc + (p.x ^ key));
-                    const float t1 = lds_f32(Tsrc + (p.y ^ key));
-                    const float t2 = lds_f32(Tsrc + (p.z ^ key));
-                    const float t3 = lds_f32(Tsrc + (p.w ^ key));
-                    if (HAS_VALS) {
-                        const uint4 v = lds_u128(val_a + e * 4);
-                        s0 = fmaf(__uint_as_float(v.x), t0, s0);
-                        s1 = fmaf(__uint_as_float(v.y), t1, s1);
-                        s0 = fmaf(__uint_as_float(v.z), t2, s0);
-                        s1 = fmaf(__uint_as_float(v.w), t3, s1);
-                    } else {
-                        s0 += t0 + t2;
-                        s1 += t1 + t3;
-                    }
-                }
-                for (; e < e1; ++e) {
-                    uint32_t p;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p) : "r"(pre_a + e * 4));
-                    const float t = lds_f32(Tsrc + (p ^ key));
-                    s1 = HAS_VALS ? fmaf(lds_f32(val_a + e * 4), t, s1) : s1 + t;
-                }
-            } else {
-                for (; e < e1; ++e) {
-                    const uint32_t j = (uint32_t)(__ldg(colidx + e) - node0);
-                    const float t = lds_f32(Tsrc + (swz_row(j) ^ key));
-                    s0 = HAS_VALS ? fmaf(__ldg(vals + e), t, s0) : s0 + t;
-                }
-            }
-            const float s = s0 + s1;
+            const float s = gather_row<HAS_VALS, STAGED>(Tsrc, rp_s[r], rp_s[r + 1], pre_a, val_a, colidx, vals, node0, key);
             const uint32_t d = Tdst + (swz_row((uint32_t)r) ^ key);
             sts_f32(d, first ? s : 2.f * s - lds_f32(d));
         }
@@ -302,8 +261,15 @@ size_t cheb_forward_smem_bytes(int rows_cap, int nnz_cap, int w_rows_cap, bool h
 template <int MT, bool HAS_VALS, bool STAGED>
 static cudaError_t launch_one(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = cheb_forward_kernel<MT, HAS_VALS, STAGED>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // the attribute is sticky per (function, device): only raise it when a launch needs more
+    static int smem_set[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((int)smem > smem_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[dev & 63] = (int)smem;
+    }
     kern<<<grid, MHO_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }

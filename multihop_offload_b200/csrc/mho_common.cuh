@@ -68,6 +68,57 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// ---------------------------------------------------------------------------------------------
+// s = sum_{e in [e0,e1)} val[e] * T[col[e]][lane]   for one operator row, one lane per feature.
+// STAGED: col ids were pre-translated to swizzled smem row offsets (pre_a), 4 per LDS.128;
+// otherwise the CSR slice is read from global memory through L1 (e0/e1 are global offsets).
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_VALS, bool STAGED>
+__device__ __forceinline__ float gather_row(uint32_t Tsrc, int e0, int e1, uint32_t pre_a, uint32_t val_a,
+                                            const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                            int node0, uint32_t key) {
+    float s0 = 0.f, s1 = 0.f;
+    int e = e0;
+    if (STAGED) {
+        for (; (e & 3) && e < e1; ++e) {  // head (unaligned)
+            uint32_t p;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p) : "r"(pre_a + e * 4));
+            const float t = lds_f32(Tsrc + (p ^ key));
+            s0 = HAS_VALS ? fmaf(lds_f32(val_a + e * 4), t, s0) : s0 + t;
+        }
+        for (; e + 4 <= e1; e += 4) {  // body: 4 pre-swizzled offsets per LDS.128
+            const uint4 p = lds_u128(pre_a + e * 4);
+            const float t0 = lds_f32(Tsrc + (p.x ^ key));
+            const float t1 = lds_f32(Tsrc + (p.y ^ key));
+            const float t2 = lds_f32(Tsrc + (p.z ^ key));
+            const float t3 = lds_f32(Tsrc + (p.w ^ key));
+            if (HAS_VALS) {
+                const uint4 v = lds_u128(val_a + e * 4);
+                s0 = fmaf(__uint_as_float(v.x), t0, s0);
+                s1 = fmaf(__uint_as_float(v.y), t1, s1);
+                s0 = fmaf(__uint_as_float(v.z), t2, s0);
+                s1 = fmaf(__uint_as_float(v.w), t3, s1);
+            } else {
+                s0 += t0 + t2;
+                s1 += t1 + t3;
+            }
+        }
+        for (; e < e1; ++e) {  // tail
+            uint32_t p;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p) : "r"(pre_a + e * 4));
+            const float t = lds_f32(Tsrc + (p ^ key));
+            s1 = HAS_VALS ? fmaf(lds_f32(val_a + e * 4), t, s1) : s1 + t;
+        }
+    } else {
+        for (; e < e1; ++e) {
+            const uint32_t j = (uint32_t)(__ldg(colidx + e) - node0);
+            const float t = lds_f32(Tsrc + (swz_row(j) ^ key));
+            s0 = HAS_VALS ? fmaf(__ldg(vals + e), t, s0) : s0 + t;
+        }
+    }
+    return s0 + s1;
+}
+
 __device__ __forceinline__ float apply_act(float z, int act, float slope) {
     if (act == MHO_ACT_RELU) return fmaxf(z, 0.f);
     if (act == MHO_ACT_LEAKY) return z > 0.f ? z : slope * z;

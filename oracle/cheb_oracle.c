@@ -18,8 +18,8 @@
 
 typedef struct { int K, f_in, f_out, act; double slope; const double* W; const double* b; } layer64_t;
 
-static void spmm(const int32_t* rp, const int32_t* ci, const double* va, int node0, int n, int F,
-                 const double* src, double* dst) {
+static void spmm(const int32_t* restrict rp, const int32_t* restrict ci, const double* restrict va, int node0, int n, int F,
+                 const double* restrict src, double* restrict dst) {
     for (int i = 0; i < n; ++i) {
         double* d = dst + (size_t)i * F;
         for (int f = 0; f < F; ++f) d[f] = 0.0;
@@ -31,14 +31,19 @@ static void spmm(const int32_t* rp, const int32_t* ci, const double* va, int nod
     }
 }
 
-static void gemm_acc(int n, int Fi, int Fo, const double* T, const double* W, double* out) {
-    for (int i = 0; i < n; ++i)
+static void gemm_acc(int n, int Fi, int Fo, const double* restrict T, const double* restrict W, double* restrict out) {
+    for (int i = 0; i < n; ++i) {
+        double acc[64];
+        double* restrict o = out + (size_t)i * Fo;
+        for (int c = 0; c < Fo; ++c) acc[c] = o[c];
         for (int f = 0; f < Fi; ++f) {
             const double t = T[(size_t)i * Fi + f];
-            const double* w = W + (size_t)f * Fo;
-            double* o = out + (size_t)i * Fo;
-            for (int c = 0; c < Fo; ++c) o[c] += t * w[c];
+            const double* restrict w = W + (size_t)f * Fo;
+#pragma GCC ivdep
+            for (int c = 0; c < Fo; ++c) acc[c] += t * w[c];
         }
+        for (int c = 0; c < Fo; ++c) o[c] = acc[c];
+    }
 }
 
 /* Returns 0 on success.  X [total_nodes, layers[0].f_in], Y [total_nodes, layers[L-1].f_out]. */

@@ -34,3 +34,22 @@ def random_weights(specs, rng, scale=1.0, bias=0.05):
         lim = np.sqrt(6.0 / (s.K * s.f_in + s.K * s.f_out)) * scale
         ws.append((rng.uniform(-lim, lim, size=(s.K, s.f_in, s.f_out)), rng.normal(size=s.f_out) * bias))
     return ws
+
+
+def numpy_fp32_forward(mats, X, weights, acts, slope=0.2):
+    """The same recurrence in plain numpy fp32 (scipy CSR @ + matmul): the error a straightforward
+    fp32 implementation makes against the fp64 oracle - the yardstick for 'fp32-grade' parity."""
+    outs, o = [], 0
+    for A in mats:
+        n = A.shape[0]
+        A32 = sp.csr_matrix(A).astype(np.float32)
+        h = X[o:o + n].astype(np.float32)
+        for (W, b), act in zip(weights, acts):
+            W = W.astype(np.float32); K = W.shape[0]
+            Ts = [h]
+            if K > 1: Ts.append(A32 @ h)
+            for _ in range(2, K): Ts.append(np.float32(2.0) * (A32 @ Ts[-1]) - Ts[-2])
+            z = sum(T @ W[k] for k, T in enumerate(Ts)) + b.astype(np.float32)
+            h = z if act == 0 else (np.maximum(z, 0) if act == 1 else np.where(z > 0, z, np.float32(slope) * z))
+        outs.append(h); o += n
+    return np.concatenate(outs, axis=0)
