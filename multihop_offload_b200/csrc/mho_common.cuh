@@ -40,6 +40,17 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
@@ -163,6 +174,9 @@ struct FwdParams {
     float* saved;     // nullable
     int rows_cap;     // multiple of 16, >= max tile rows
     int nnz_cap;      // staged nnz capacity (multiple of 4); 0 => read CSR from global memory
-    int w_rows_cap;   // rows (of 128 B) of one W image = max_l K_l * pad8(f_out_l)
+    int w_rows_cap;   // rows (of 128 B) of the fp32 W image region
+    int w_resident;   // 1: every layer's image stays in smem for the CTA's lifetime; 0: restaged per layer per tile
+    int w_row_off[MHO_MAX_LAYERS];  // first image row of each layer (w_resident) else 0
+    int prefetch;     // 1: third tile buffer + second CSR staging set, next tile fetched with cp.async
     int total_nodes;
 };

@@ -5,27 +5,37 @@ import scipy.sparse as sp
 import chebnet_oracle as O
 
 
-def rel_err(y, ref, per_graph_off=None):
-    """max over graphs of |y-ref|_inf / max(|ref|_inf per graph, tiny)  (SURVEY 7.2)."""
+def rel_err(y, ref, per_graph_off=None, scale=None):
+    """max over graphs of |y-ref|_inf / max(|ref|_inf per graph, scale_g, tiny)  (SURVEY 7.2).
+
+    `scale` (optional, one value per graph) is the inf-norm of the last layer's PRE-activation:
+    a relu output that is (almost) entirely dead has |y_ref| << |z_ref|, and an error of one fp32
+    ulp of z would otherwise read as a huge "relative" error of y ("relu outputs that
+    are exactly 0 in one and 1e-9 in the other must not fail a pure-relative check")."""
     y = np.asarray(y, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     if per_graph_off is None:
-        return np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30)
+        den = max(np.abs(ref).max(), 1e-30 if scale is None else float(np.max(scale)))
+        return np.abs(y - ref).max() / den
     worst = 0.0
-    for a, b in zip(per_graph_off[:-1], per_graph_off[1:]):
+    for g, (a, b) in enumerate(zip(per_graph_off[:-1], per_graph_off[1:])):
         if b > a:
-            den = max(np.abs(ref[a:b]).max(), 1e-30)
+            den = max(np.abs(ref[a:b]).max(), 1e-30, 0.0 if scale is None else float(scale[g]))
             worst = max(worst, np.abs(y[a:b] - ref[a:b]).max() / den)
     return worst
 
 
-def oracle_batch_forward(mats, X, weights, acts=None, slope=0.2):
-    """Reference semantics: ONE GRAPH AT A TIME (gnn_offloading_agent.py:149), fp64."""
-    outs, o = [], 0
+def oracle_batch_forward(mats, X, weights, acts=None, slope=0.2, return_scale=False):
+    """Reference semantics: ONE GRAPH AT A TIME (gnn_offloading_agent.py:149), fp64.
+    return_scale: also the per-graph inf-norm of the last layer's pre-activation."""
+    outs, scales, o = [], [], 0
     for A in mats:
         n = A.shape[0]
-        outs.append(O.cheb_stack_forward(A, X[o:o + n], weights, acts, slope))
+        y, cache = O.cheb_stack_forward(A, X[o:o + n], weights, acts, slope, return_cache=True)
+        outs.append(y)
+        scales.append(np.abs(cache[-1][1]).max() if n else 0.0)
         o += n
-    return np.concatenate(outs, axis=0)
+    Y = np.concatenate(outs, axis=0)
+    return (Y, np.asarray(scales)) if return_scale else Y
 
 
 def random_weights(specs, rng, scale=1.0, bias=0.05):
