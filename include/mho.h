@@ -64,6 +64,8 @@ typedef struct {
     /* tile plan (from mho_plan_tiles): tile t = graphs [tile_off[t], tile_off[t+1]) processed
        by one CTA; NULL => one graph per tile */
     const int32_t* tile_off;   /* [n_tiles+1] graph indices, device */
+    const int32_t* tile_info;  /* optional [n_tiles][4] = {node0, rows, nz0, nnz} (device, 16 B aligned):
+                                  saves the kernel three dependent loads per tile; NULL => derived */
     int32_t n_tiles;
     int32_t max_tile_rows;     /* max over tiles of the node count (host-known) */
     int32_t max_tile_nnz;      /* max over tiles of the nnz count (host-known) */
@@ -88,6 +90,11 @@ int mho_version(void);
 /* number of kernels launched through this context so far (bench.py's gpu_launches claim) */
 int64_t mho_launch_count(const mho_ctx_t* ctx);
 
+/* The forward snapshots the weights of a layer set into packed TF32 hi/lo images the first time it sees
+ * a given set of (W, b) pointers and reuses them afterwards.  Call this after modifying weights IN PLACE
+ * behind the library's back (mho_adam_replay does it itself). */
+int mho_invalidate_weights(mho_ctx_t* ctx);
+
 /* ---- host-side planning helper (pure CPU, no CUDA): greedy packing of consecutive graphs
  * into tiles of at most tile_rows nodes.  graph_off_host/rowptr_host are HOST copies.
  * tile_off_host must have room for n_graphs+1 entries.  Graphs larger than tile_rows get a
@@ -95,6 +102,9 @@ int64_t mho_launch_count(const mho_ctx_t* ctx);
 int mho_plan_tiles(const int32_t* graph_off_host, const int32_t* rowptr_host, int32_t n_graphs,
                    int32_t tile_rows, int32_t* tile_off_host, int32_t* n_tiles,
                    int32_t* max_tile_rows, int32_t* max_tile_nnz);
+/* tile_info_host [n_tiles][4] from a plan (tile_off_host NULL => one graph per tile) */
+int mho_fill_tile_info(const int32_t* graph_off_host, const int32_t* rowptr_host, const int32_t* tile_off_host,
+                       int32_t n_tiles, int32_t* tile_info_host);
 
 /* ---- forward: replaces ACOAgent.predict -> self.model([x_in, a_in])
  * (gnn_offloading_agent.py:144-150) for a whole batch.  X [total_nodes, layers[0].f_in],

@@ -87,6 +87,12 @@ class GraphBatch:
                    "mho_plan_tiles")
         self.n_tiles, self.max_tile_rows, self.max_tile_nnz = nt.value, mr.value, mz.value
         self.tile_off = tile_off[: self.n_tiles + 1].copy()
+        self.tile_info = np.zeros((max(self.n_tiles, 1), 4), dtype=np.int32)
+        self.graph_info = np.zeros((max(self.n_graphs, 1), 4), dtype=np.int32)
+        _lib.check(lib.mho_fill_tile_info(self.graph_off.ctypes.data, self.rowptr.ctypes.data, self.tile_off.ctypes.data,
+                                          self.n_tiles, self.tile_info.ctypes.data), "mho_fill_tile_info")
+        _lib.check(lib.mho_fill_tile_info(self.graph_off.ctypes.data, self.rowptr.ctypes.data, None,
+                                          self.n_graphs, self.graph_info.ctypes.data), "mho_fill_tile_info")
         # one-graph-per-tile statistics (the backward runs one graph per CTA)
         if self.n_graphs:
             sizes = np.diff(self.graph_off)
@@ -106,7 +112,7 @@ class GraphBatch:
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
         self.dev = dict(graph_off=up(self.graph_off), rowptr=up(self.rowptr), colidx=up(self.colidx),
-                        tile_off=up(self.tile_off))
+                        tile_off=up(self.tile_off), tile_info=up(self.tile_info), graph_info=up(self.graph_info))
         if self.vals is not None:
             self.dev["vals"] = up(self.vals)
         if self.transpose is not None:
@@ -138,9 +144,11 @@ class GraphBatch:
             b.vals_t = self.dev["vals_t"].data_ptr() if "vals" in self.dev else None
         if per_graph_tiles:
             b.tile_off, b.n_tiles = None, self.n_graphs
+            b.tile_info = self.dev["graph_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_graph_rows, self.max_graph_nnz
         else:
             b.tile_off, b.n_tiles = self.dev["tile_off"].data_ptr(), self.n_tiles
+            b.tile_info = self.dev["tile_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_tile_rows, self.max_tile_nnz
         return b
 

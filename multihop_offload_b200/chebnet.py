@@ -78,6 +78,11 @@ class ChebNet:
         flat = np.ascontiguousarray(np.asarray(flat, dtype=np.float32).ravel())
         assert flat.size == self.n_params, (flat.size, self.n_params)
         self.params.copy_(torch.from_numpy(flat))
+        self.weights_changed()
+
+    def weights_changed(self):
+        """Tell libmho the parameter buffer was modified in place (packed weight images are stale)."""
+        self.ctx.lib.mho_invalidate_weights(self.ctx.handle)
 
     def get_flat(self):
         return self.params.detach().cpu().numpy().astype(np.float64)

@@ -291,7 +291,7 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     BwdParams p;
     memset(&p, 0, sizeof(p));
     p.b.graph_off = b->graph_off; p.b.rowptr = b->rowptr; p.b.colidx = b->colidx; p.b.vals = b->vals;
-    p.b.tile_off = nullptr; p.b.n_graphs = b->n_graphs; p.b.n_tiles = b->n_graphs;
+    p.b.tile_off = nullptr; p.b.tile_info = nullptr; p.b.n_graphs = b->n_graphs; p.b.n_tiles = b->n_graphs;
     p.rowptr_t = b->rowptr_t; p.colidx_t = b->colidx_t; p.vals_t = b->vals_t;
     p.n_layers = n_layers;
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);

@@ -19,7 +19,15 @@
 //     3xTF32 split in registers for fp32-grade accuracy) straight out of the same tiles via
 //     ldmatrix, interleaved with the sparse step for T_{k+1};
 //   * HBM traffic per tile is exactly X in, Y out, CSR once; T_k never leaves the SM.
+#include <cstdlib>
+
 #include "mho_common.cuh"
+
+// the forward kernel runs 16 warps per CTA: two CTAs per SM then give 32 resident warps, which this
+// latency-bound kernel needs; the dense part maps warp w -> m-tile slot (w & 7), n-tile half (w >> 3)
+#define FWD_THREADS 512
+#define FWD_NWARPS (FWD_THREADS / 32)
+#define FWD_MSLOTS (FWD_NWARPS / 2)
 
 struct TileInfo {
     int node0, rows, nz0, nnz;
@@ -27,6 +35,11 @@ struct TileInfo {
 
 __device__ __forceinline__ TileInfo load_tile_info(const BatchDev& b, int tile) {
     TileInfo t;
+    if (b.tile_info != nullptr) {  // one 16 B load instead of three dependent ones
+        const int4 v = __ldg(reinterpret_cast<const int4*>(b.tile_info) + tile);
+        t.node0 = v.x; t.rows = v.y; t.nz0 = v.z; t.nnz = v.w;
+        return t;
+    }
     const int g0 = b.tile_off ? __ldg(b.tile_off + tile) : tile;
     const int g1 = b.tile_off ? __ldg(b.tile_off + tile + 1) : tile + 1;
     t.node0 = __ldg(b.graph_off + g0);
@@ -38,120 +51,206 @@ __device__ __forceinline__ TileInfo load_tile_info(const BatchDev& b, int tile) 
 }
 
 // -------------------------------------------------------------------------------------------
-// Stage one layer's weights: Keras layout W[k][f][o] -> transposed swizzled fp32 image
-// Wt[(k*fo_pad + o)][f] (128 B rows) so that ldmatrix yields mma B fragments; the TF32 hi/lo
-// split happens in registers at use.
+// Weight preparation (one tiny launch whenever the weights changed): Keras layout W[k][f][o] ->
+// per layer a block of 128 B rows  [hi image: K*fo_pad rows][lo image: K*fo_pad rows][bias: 1 row]
+// where image row (k*fo_pad + o) holds W[k][.][o] over f (transposed, 128B-swizzled on o) split into
+// TF32 hi / lo parts (cvt.rna), so that a CTA stages it with straight 16 B cp.async copies and
+// ldmatrix yields ready-to-use mma B fragments.
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_weights(const LayerDev& L, unsigned char* wimg, float* bias_s, int tid) {
-    const int fo_pad = pad8(L.f_out), fi_pad = pad8(L.f_in);
-    const int per_k = fi_pad * fo_pad;
-    const int total = L.K * per_k;
-    for (int idx = tid; idx < total; idx += MHO_THREADS) {
-        const int k = idx / per_k, rem = idx - k * per_k;
-        const int f = rem / fo_pad, o = rem - f * fo_pad;
-        float w = 0.f;
-        if (f < L.f_in && o < L.f_out) w = __ldg(L.W + ((size_t)k * L.f_in + f) * L.f_out + o);
-        *reinterpret_cast<float*>(wimg + (uint32_t)(k * fo_pad) * 128u + swz_off((uint32_t)o, (uint32_t)f)) = w;
+struct PrepParams {
+    int n_layers;
+    LayerDev layers[MHO_MAX_LAYERS];
+    int row_off[MHO_MAX_LAYERS];
+    unsigned char* out;
+};
+
+__global__ void prepare_weights_kernel(const __grid_constant__ PrepParams p) {
+    for (int l = blockIdx.y; l < p.n_layers; l += gridDim.y) {
+        const LayerDev& L = p.layers[l];
+        const int fo_pad = pad8(L.f_out);
+        const int n_rows = L.K * fo_pad;
+        unsigned char* hi_img = p.out + (size_t)p.row_off[l] * 128;
+        unsigned char* lo_img = hi_img + (size_t)n_rows * 128;
+        float* bias = reinterpret_cast<float*>(lo_img + (size_t)n_rows * 128);
+        const int total = n_rows * 32;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+            // o fastest: coalesced reads of W[k][f][.]
+            const int k = idx / (fo_pad * 32), rem = idx - k * fo_pad * 32;
+            const int f = rem / fo_pad, o = rem - f * fo_pad;
+            float w = 0.f;
+            if (f < L.f_in && o < L.f_out) w = __ldg(L.W + ((size_t)k * L.f_in + f) * L.f_out + o);
+            uint32_t hi, lo;
+            split_tf32(w, hi, lo);
+            const uint32_t off = (uint32_t)(k * fo_pad) * 128u + swz_off((uint32_t)o, (uint32_t)f);
+            *reinterpret_cast<uint32_t*>(hi_img + off) = hi;
+            *reinterpret_cast<uint32_t*>(lo_img + off) = lo;
+        }
+        if (blockIdx.x == 0 && threadIdx.x < 32)
+            bias[threadIdx.x] = (L.b != nullptr && (int)threadIdx.x < L.f_out) ? __ldg(L.b + threadIdx.x) : 0.f;
     }
-    if (tid < 32) bias_s[tid] = (L.b != nullptr && tid < L.f_out) ? __ldg(L.b + tid) : 0.f;
+}
+
+int wprep_layer_rows(int K, int f_out) { return 2 * K * pad8(f_out) + 1; }
+
+cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const int* row_off, unsigned char* out,
+                                   cudaStream_t st) {
+    PrepParams p;
+    p.n_layers = n_layers;
+    for (int l = 0; l < n_layers; ++l) { p.layers[l] = layers[l]; p.row_off[l] = row_off[l]; }
+    p.out = out;
+    dim3 grid(8, n_layers);
+    prepare_weights_kernel<<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// copy one layer's prepared block (hi, lo, bias) into shared memory with 16 B cp.async
+__device__ __forceinline__ void stage_weights_async(const FwdParams& p, int l, uint32_t dst, int tid) {
+    const int rows = 2 * p.layers[l].K * pad8(p.layers[l].f_out) + 1;
+    const unsigned char* src = p.wprep + (size_t)p.wprep_row_off[l] * 128;
+    for (int c = tid; c < rows * 8; c += FWD_THREADS) cp_async16(dst + (uint32_t)c * 16u, src + (size_t)c * 16);
 }
 
 // -------------------------------------------------------------------------------------------
 // acc[nt][4] += T[row0..row0+15][0..fi_pad) . W_k   (3xTF32: lo*hi + hi*lo + hi*hi, fp32 accumulate)
+// A is split in registers (5 integer/float ops per element), W comes pre-split from the images.
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_tile(float (&acc)[4][4], uint32_t T_addr, int row0, uint32_t w_k, int nchunks,
-                                         int nnt, int lane) {
+__device__ __forceinline__ void mma_tile(float (&acc)[2][4], uint32_t T_addr, int row0, uint32_t whi_k, uint32_t wlo_k,
+                                         int nchunks, int nt0, int nnt, int lane) {
     const uint32_t arow = (uint32_t)row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
     const uint32_t a_base = T_addr + (arow << 7);
     const uint32_t a_key = arow & 7u;
     const uint32_t a_sel = (uint32_t)(lane >> 4);        // 0: chunk 2c, 1: chunk 2c+1
     const uint32_t b_r = (uint32_t)(lane & 7);
     const uint32_t b_sel = (uint32_t)((lane >> 3) & 1);  // k half
-    const uint32_t b_nt = (uint32_t)(lane >> 4);         // which n-tile of the pair
-#pragma unroll 1
+    uint32_t o_nt = (uint32_t)nt0 + (uint32_t)(lane >> 4);  // which n-tile of this warp's pair
+    if ((int)o_nt >= nnt) o_nt = (uint32_t)(nnt - 1);       // odd n-tile count: duplicate, result unused
+    const uint32_t boff = ((o_nt * 8u + b_r) << 7);
+    const bool two = (nt0 + 1 < nnt);
+#pragma unroll 2
     for (int c = 0; c < nchunks; ++c) {
-        uint32_t a[4], ah[4], al[4];
+        uint32_t a[4], ah[4], al[4], bh[4], bl[4];
         ldmatrix_x4(a_base + ((((uint32_t)(2 * c) + a_sel) ^ a_key) << 4), a[0], a[1], a[2], a[3]);
+        const uint32_t bch = ((((uint32_t)(2 * c) + b_sel) ^ b_r) << 4);  // (o & 7) == b_r
+        ldmatrix_x4(whi_k + boff + bch, bh[0], bh[1], bh[2], bh[3]);
+        ldmatrix_x4(wlo_k + boff + bch, bl[0], bl[1], bl[2], bl[3]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(__uint_as_float(a[i]), ah[i], al[i]);
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-            if (np * 2 < nnt) {
-                uint32_t o_nt = (uint32_t)(np * 2) + b_nt;
-                if ((int)o_nt >= nnt) o_nt = (uint32_t)(nnt - 1);  // odd n-tile count: duplicate, result unused
-                const uint32_t o = o_nt * 8u + b_r;
-                uint32_t b[4], bh[4], bl[4];
-                ldmatrix_x4(w_k + (o << 7) + ((((uint32_t)(2 * c) + b_sel) ^ (o & 7u)) << 4), b[0], b[1], b[2], b[3]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32(__uint_as_float(b[i]), bh[i], bl[i]);
-                mma_tf32(acc[np * 2], al, bh[0], bh[1]);
-                mma_tf32(acc[np * 2], ah, bl[0], bl[1]);
-                mma_tf32(acc[np * 2], ah, bh[0], bh[1]);
-                if (np * 2 + 1 < nnt) {
-                    mma_tf32(acc[np * 2 + 1], al, bh[2], bh[3]);
-                    mma_tf32(acc[np * 2 + 1], ah, bl[2], bl[3]);
-                    mma_tf32(acc[np * 2 + 1], ah, bh[2], bh[3]);
-                }
-            }
+        for (int i = 0; i < 4; ++i) split_tf32_fast(__uint_as_float(a[i]), ah[i], al[i]);
+        mma_tf32(acc[0], al, bh[0], bh[1]);
+        mma_tf32(acc[0], ah, bl[0], bl[1]);
+        mma_tf32(acc[0], ah, bh[0], bh[1]);
+        if (two) {
+            mma_tf32(acc[1], al, bh[2], bh[3]);
+            mma_tf32(acc[1], ah, bl[2], bl[3]);
+            mma_tf32(acc[1], ah, bh[2], bh[3]);
         }
     }
 }
 
 // -------------------------------------------------------------------------------------------
-// Sparse recurrence step, stream form.  The warp owns rows [rb, re) and walks their entries
+// Sparse recurrence step, stream form, perfectly balanced.  The tile's entry stream is cut into
+// 4*NWARPS equal SEGMENTS regardless of row boundaries; a warp is 4 groups of 8 lanes, each group
+// walks one segment, one entry per step, each lane holding 4 features (one 16 B chunk): one LDS.128
+// per lane = one full 128 B row per group = 4 neighbour gathers per warp instruction, each a
+// conflict-free quarter-warp wavefront.
 //   first step : Tdst[r] = sum_j A[r,j] Tsrc[j]
 //   later steps: Tdst[r] = 2 sum_j A[r,j] Tsrc[j] - Tdst[r]      (T_{k+1} overwrites T_{k-1})
+// Rows that straddle segments (hub rows!) are finished in spmm_fixup after a barrier: a group
+// that starts mid-row keeps the partial sum of its first row ("head"), every group publishes the
+// partial sum after its last row end ("leftover") in shared memory.
 // stream word = swizzled smem row offset | bit0 (last entry of its row) | bit1 (next row(s) empty).
 // rp_s holds the RAW global row pointers of the tile (subtract nz0).
 // -------------------------------------------------------------------------------------------
+struct SegInfo {
+    int sb, n;      // first entry and entry count of this group's segment
+    int r0;         // row containing entry sb
+    int mid;        // segment starts in the middle of row r0
+    int seg_len;    // nominal segment length L (entry e belongs to group e / L)
+};
+
+struct HeadState {
+    float4 head;
+    int head_row;
+    int pending;    // 1: the head row's sum is still in `head` and must be completed by spmm_fixup
+};
+
+__device__ __forceinline__ void emit_row(uint32_t Tdst, int row, uint32_t ckey, bool first, const float4& acc) {
+    const uint32_t d = Tdst + (swz_row((uint32_t)row) ^ ckey);
+    float4 o = acc;
+    if (!first) {
+        const float4 q = lds_f128(d);
+        o = make_float4(2.f * acc.x - q.x, 2.f * acc.y - q.y, 2.f * acc.z - q.z, 2.f * acc.w - q.w);
+    }
+    sts_f128(d, o);
+}
+
+__device__ __forceinline__ void emit_empty_rows(uint32_t Tdst, int& row, int rows, const int* rp_s, uint32_t ckey, bool first) {
+    while (row < rows && rp_s[row + 1] == rp_s[row]) {
+        emit_row(Tdst, row, ckey, first, make_float4(0.f, 0.f, 0.f, 0.f));
+        ++row;
+    }
+}
+
 template <bool HAS_VALS>
-__device__ __forceinline__ void spmm_walk(uint32_t Tsrc, uint32_t Tdst, bool first, int rb, int re, const int* rp_s,
-                                          int nz0, uint32_t pre_a, uint32_t val_a, uint32_t key) {
-    int row = rb;
-    float acc = 0.f;
-    auto emit_empty_run = [&]() {
-        while (row < re && rp_s[row + 1] == rp_s[row]) {
-            const uint32_t d = Tdst + (swz_row((uint32_t)row) ^ key);
-            sts_f32(d, first ? 0.f : -lds_f32(d));
-            ++row;
-        }
-    };
-    auto step = [&](uint32_t pw, float t, float v) {
-        acc = HAS_VALS ? fmaf(v, t, acc) : acc + t;
-        if (pw & 1u) {
-            const uint32_t d = Tdst + (swz_row((uint32_t)row) ^ key);
-            sts_f32(d, first ? acc : 2.f * acc - lds_f32(d));
-            acc = 0.f;
-            ++row;
-            if (pw & 2u) emit_empty_run();
-        }
-    };
-    emit_empty_run();
-    if (row >= re) return;
-    int e = rp_s[row] - nz0;
-    const int ee = rp_s[re] - nz0;
-    for (; (e & 3) && e < ee; ++e) {  // head: up to the next 16 B boundary of the stream
-        const uint32_t pw = lds_u32(pre_a + e * 4);
-        const float t = lds_f32(Tsrc + ((pw & ~3u) ^ key));
-        step(pw, t, HAS_VALS ? lds_f32(val_a + e * 4) : 1.f);
+__device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, bool first, const SegInfo& sg, int rows,
+                                              const int* rp_s, uint32_t pre_a, uint32_t val_a, uint32_t ckey,
+                                              uint32_t left_a, bool is_group0, HeadState& hs) {
+    hs.pending = 0;
+    hs.head_row = 0;
+    hs.head = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (is_group0) {  // empty rows in front of the first stored entry belong to nobody's stream
+        int r = 0;
+        emit_empty_rows(Tdst, r, rows, rp_s, ckey, first);
     }
-    for (; e + 4 <= ee; e += 4) {  // body: 4 stream words per LDS.128, 4 gathers in flight
-        const uint4 pw = lds_u128(pre_a + e * 4);
-        const float t0 = lds_f32(Tsrc + ((pw.x & ~3u) ^ key));
-        const float t1 = lds_f32(Tsrc + ((pw.y & ~3u) ^ key));
-        const float t2 = lds_f32(Tsrc + ((pw.z & ~3u) ^ key));
-        const float t3 = lds_f32(Tsrc + ((pw.w & ~3u) ^ key));
-        uint4 vv = make_uint4(0, 0, 0, 0);
-        if (HAS_VALS) vv = lds_u128(val_a + e * 4);
-        step(pw.x, t0, __uint_as_float(vv.x));
-        step(pw.y, t1, __uint_as_float(vv.y));
-        step(pw.z, t2, __uint_as_float(vv.z));
-        step(pw.w, t3, __uint_as_float(vv.w));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sg.n > 0) {
+        int row = sg.r0;
+        int waiting = sg.mid;  // the first row end seen closes a row that started in an earlier segment
+        uint32_t ea = pre_a + (uint32_t)sg.sb * 4u, va = val_a + (uint32_t)sg.sb * 4u;
+        uint32_t pw = lds_u32(ea);
+        float vv = HAS_VALS ? lds_f32(va) : 1.f;
+        for (int s = 0; s < sg.n; ++s) {
+            const uint32_t cur = pw;
+            const float cv = vv;
+            ea += 4; va += 4;
+            if (s + 1 < sg.n) {  // next step's stream word is in flight during the gather
+                pw = lds_u32(ea);
+                if (HAS_VALS) vv = lds_f32(va);
+            }
+            const float4 t = lds_f128(Tsrc + ((cur & ~3u) ^ ckey));
+            if (HAS_VALS) {
+                acc.x = fmaf(cv, t.x, acc.x); acc.y = fmaf(cv, t.y, acc.y);
+                acc.z = fmaf(cv, t.z, acc.z); acc.w = fmaf(cv, t.w, acc.w);
+            } else {
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+            if (cur & 1u) {
+                if (waiting) {
+                    hs.head = acc; hs.head_row = row; hs.pending = 1;
+                    waiting = 0;
+                } else {
+                    emit_row(Tdst, row, ckey, first, acc);
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                ++row;
+                if (cur & 2u) emit_empty_rows(Tdst, row, rows, rp_s, ckey, first);
+            }
+        }
     }
-    for (; e < ee; ++e) {  // tail
-        const uint32_t pw = lds_u32(pre_a + e * 4);
-        const float t = lds_f32(Tsrc + ((pw & ~3u) ^ key));
-        step(pw, t, HAS_VALS ? lds_f32(val_a + e * 4) : 1.f);
+    sts_f128(left_a, acc);  // partial sum of the row still open at the end of the segment (0 if none)
+}
+
+// after a barrier: complete the rows that straddled segment boundaries (deterministic order)
+__device__ __forceinline__ void spmm_fixup(uint32_t Tdst, bool first, const SegInfo& sg, int group, const int* rp_s, int nz0,
+                                           uint32_t ckey, uint32_t left_base, const HeadState& hs) {
+    if (hs.pending) {
+        const int j0 = (rp_s[hs.head_row] - nz0) / sg.seg_len;  // group holding the row's first entry
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = j0; j < group; ++j) {
+            const float4 q = lds_f128(left_base + (uint32_t)j * 128u + ckey);
+            tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
+        }
+        tot.x += hs.head.x; tot.y += hs.head.y; tot.z += hs.head.z; tot.w += hs.head.w;
+        emit_row(Tdst, hs.head_row, ckey, first, tot);
     }
 }
 
@@ -160,7 +259,7 @@ template <bool HAS_VALS>
 __device__ __forceinline__ void spmm_rows_global(uint32_t Tsrc, uint32_t Tdst, bool first, int rows, const int* rp_s,
                                                  const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                  int node0, int warp, uint32_t key) {
-    for (int r = warp; r < rows; r += MHO_NWARPS) {
+    for (int r = warp; r < rows; r += FWD_NWARPS) {
         const float s = gather_row<HAS_VALS, false>(Tsrc, rp_s[r], rp_s[r + 1], 0, 0, colidx, vals, node0, key);
         const uint32_t d = Tdst + (swz_row((uint32_t)r) ^ key);
         sts_f32(d, first ? s : 2.f * s - lds_f32(d));
@@ -180,17 +279,17 @@ __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileI
         const float* src = p.X + (size_t)t.node0 * fi;
         const int total = t.rows * cpr;
         if (cpr == 8) {
-            for (int c = tid; c < total; c += MHO_THREADS) {
+            for (int c = tid; c < total; c += FWD_THREADS) {
                 const uint32_t r = (uint32_t)c >> 3, ch = (uint32_t)c & 7u;
                 cp_async16(Tbuf + (r << 7) + ((ch ^ (r & 7u)) << 4), src + (size_t)c * 4);
             }
         } else {
-            for (int c = tid; c < total; c += MHO_THREADS) {
+            for (int c = tid; c < total; c += FWD_THREADS) {
                 const uint32_t r = (uint32_t)(c / cpr), ch = (uint32_t)(c - (int)r * cpr);
                 cp_async16(Tbuf + (r << 7) + ((ch ^ (r & 7u)) << 4), src + (size_t)c * 4);
             }
             if (cpr & 1) {  // f_in = 4 (mod 8): zero the pad chunk so columns [f_in, pad8(f_in)) are defined
-                for (int r = tid; r < t.rows; r += MHO_THREADS) {
+                for (int r = tid; r < t.rows; r += FWD_THREADS) {
                     const uint32_t a = Tbuf + ((uint32_t)r << 7) + ((((uint32_t)cpr) ^ ((uint32_t)r & 7u)) << 4);
                     asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u));
                 }
@@ -198,14 +297,14 @@ __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileI
         }
     } else {
         const int fi_pad = pad8(fi);
-        for (int idx = tid; idx < t.rows * fi_pad; idx += MHO_THREADS) {
+        for (int idx = tid; idx < t.rows * fi_pad; idx += FWD_THREADS) {
             const int r = idx / fi_pad, c = idx - r * fi_pad;
             sts_f32(Tbuf + swz_off((uint32_t)r, (uint32_t)c), c < fi ? __ldg(p.X + (size_t)(t.node0 + r) * fi + c) : 0.f);
         }
     }
-    for (int i = tid; i <= t.rows; i += MHO_THREADS) cp_async4(rp_a + i * 4, p.b.rowptr + t.node0 + i);
+    for (int i = tid; i <= t.rows; i += FWD_THREADS) cp_async4(rp_a + i * 4, p.b.rowptr + t.node0 + i);
     if (STAGED) {
-        for (int e = tid; e < t.nnz; e += MHO_THREADS) {
+        for (int e = tid; e < t.nnz; e += FWD_THREADS) {
             cp_async4(pre_a + e * 4, p.b.colidx + t.nz0 + e);
             if (HAS_VALS) cp_async4(val_a + e * 4, p.b.vals + t.nz0 + e);
         }
@@ -213,35 +312,38 @@ __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileI
 }
 
 template <int MT, bool HAS_VALS, bool STAGED>
-__global__ void __launch_bounds__(MHO_THREADS, (MT == 1 ? 3 : (MT == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(FWD_THREADS, (MT == 1 ? 2 : 1))
 cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t key = swz_key((uint32_t)lane);
+    const uint32_t key = swz_key((uint32_t)lane);        // lane = feature layout (global-CSR fallback)
+    const uint32_t ckey = ((uint32_t)lane & 7u) << 4;    // lane = 16 B chunk layout (stream walk)
 
     // ---- shared memory carve-up
     const uint32_t tile_bytes = (uint32_t)p.rows_cap * 128u;
     const int n_tbuf = p.prefetch ? 3 : 2;
-    unsigned char* Wimg = smem + (size_t)n_tbuf * tile_bytes;
-    float* bias_all = reinterpret_cast<float*>(Wimg + (size_t)p.w_rows_cap * 128);
-    const int n_bias = p.w_resident ? p.n_layers : 1;
-    int* csr0 = reinterpret_cast<int*>(bias_all + 32 * n_bias);
+    unsigned char* Wimg = smem + (size_t)n_tbuf * tile_bytes;  // per layer: [hi rows][lo rows][bias row]
+    unsigned char* left_s = Wimg + (size_t)p.w_rows_cap * 128;  // 4*NWARPS leftover slots of 128 B
+    int* csr0 = reinterpret_cast<int*>(left_s + 4 * FWD_NWARPS * 128);
     const int rp_words = (p.rows_cap + 2 + 3) & ~3;
     const int csr_words = rp_words + p.nnz_cap * (HAS_VALS ? 2 : 1);
     const uint32_t smem_a = smem_u32(smem);
     const uint32_t w_a = smem_u32(Wimg);
     const uint32_t csr_a0 = smem_u32(csr0);
+    const uint32_t left_base = smem_u32(left_s);
+    const int group = warp * 4 + (lane >> 3);
+    const uint32_t left_a = left_base + (uint32_t)group * 128u + ckey;
 
     // rotating tile buffers: bx = T_0 / X of the current tile, bs = scratch, bp = prefetch target
     uint32_t bx = smem_a, bs = smem_a + tile_bytes, bp = smem_a + 2u * tile_bytes;
     int cs = 0;  // CSR staging set of the current tile
 
+    // resident weights ride in the first cp.async group (waited for before the first tile computes)
     if (p.w_resident)
-        for (int l = 0; l < p.n_layers; ++l)
-            stage_weights(p.layers[l], Wimg + (size_t)p.w_row_off[l] * 128, bias_all + 32 * l, tid);
+        for (int l = 0; l < p.n_layers; ++l) stage_weights_async(p, l, w_a + (uint32_t)p.w_row_off[l] * 128u, tid);
 
     int tile = blockIdx.x;
-    if (tile >= p.b.n_tiles) return;
+    if (tile >= p.b.n_tiles) { cp_async_wait<0>(); return; }
     TileInfo cur = load_tile_info(p.b, tile);
     TileInfo nxt = cur;
     bool has_nxt = (tile + (int)gridDim.x) < p.b.n_tiles;
@@ -276,65 +378,93 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 
         const int rows = cur.rows, node0 = cur.node0, nz0 = cur.nz0;
         const int n_mtiles = (rows + 15) >> 4;
-        int rb = 0, re = 0;
+        SegInfo sg;
+        sg.sb = 0; sg.n = 0; sg.r0 = 0; sg.mid = 0; sg.seg_len = 1;
         if (STAGED) {
-            // column ids -> swizzled smem row offsets, with row-end / next-row-empty flags
-            for (int r = tid; r < rows; r += MHO_THREADS) {
-                const int e0 = rp_s[r] - nz0, e1 = rp_s[r + 1] - nz0;
-                const bool next_empty = (r + 1 < rows) && (rp_s[r + 2] == rp_s[r + 1]);
-                for (int e = e0; e < e1; ++e) {
-                    uint32_t w = swz_row(lds_u32(pre_a + e * 4) - (uint32_t)node0);
-                    if (e == e1 - 1) w |= 1u | (next_empty ? 2u : 0u);
-                    sts_u32(pre_a + e * 4, w);
-                }
-            }
-            // nnz-balanced contiguous row chunks: lane l finds boundary l of cost(r) = nnz_before(r) + 2 r
+            // column ids -> swizzled smem row offsets (one thread per entry) ...
+            for (int e = tid; e < cur.nnz; e += FWD_THREADS)
+                sts_u32(pre_a + e * 4, swz_row(lds_u32(pre_a + e * 4) - (uint32_t)node0));
+            // ... the group's segment of the entry stream and the row it starts in ...
             {
-                const int total = cur.nnz + 2 * rows;
-                const int target = lane <= MHO_NWARPS ? (int)(((long long)total * lane) / MHO_NWARPS) : 0;
-                int lo = 0, hi = rows;
+                const int L = (cur.nnz + 4 * FWD_NWARPS - 1) / (4 * FWD_NWARPS);
+                sg.seg_len = L > 0 ? L : 1;
+                const int sb = min(group * sg.seg_len, cur.nnz);
+                sg.sb = sb;
+                sg.n = min(sg.seg_len, cur.nnz - sb);
+                int lo = 0, hi = rows;  // largest r with rp[r] - nz0 <= sb  (== row containing sb when n > 0)
                 while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if ((rp_s[mid] - nz0) + 2 * mid < target) lo = mid + 1; else hi = mid;
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rp_s[mid] - nz0 <= sb) lo = mid; else hi = mid - 1;
                 }
-                rb = __shfl_sync(0xffffffffu, lo, warp);
-                re = __shfl_sync(0xffffffffu, lo, warp + 1);
+                sg.r0 = lo;
+                sg.mid = (sg.n > 0 && (rp_s[lo] - nz0) < sb) ? 1 : 0;
+            }
+            __syncthreads();
+            // ... then the row-end / next-row-empty flags (one thread per row)
+            for (int r = tid; r < rows; r += FWD_THREADS) {
+                const int e1 = rp_s[r + 1] - nz0;
+                if (e1 > rp_s[r] - nz0) {
+                    const bool next_empty = (r + 1 < rows) && (rp_s[r + 2] == rp_s[r + 1]);
+                    const uint32_t a = pre_a + (uint32_t)(e1 - 1) * 4u;
+                    sts_u32(a, lds_u32(a) | 1u | (next_empty ? 2u : 0u));
+                }
             }
             __syncthreads();
         }
 
         for (int li = 0; li < p.n_layers; ++li) {
             const LayerDev& L = p.layers[li];
-            float* bias_s = bias_all + (p.w_resident ? 32 * li : 0);
-            uint32_t w_l = w_a + (uint32_t)(p.w_resident ? p.w_row_off[li] : 0) * 128u;
+            const int fi_pad = pad8(L.f_in), fo_pad = pad8(L.f_out);
+            const int nchunks = fi_pad >> 3, nnt = fo_pad >> 3;
+            const int w_rows_l = L.K * fo_pad;
+            const int w_row0 = p.w_resident ? p.w_row_off[li] : 0;
+            const uint32_t w_l = w_a + (uint32_t)w_row0 * 128u;
+            const float* bias_s = reinterpret_cast<const float*>(Wimg + (size_t)(w_row0 + 2 * w_rows_l) * 128);
             if (!p.w_resident) {
-                stage_weights(L, Wimg, bias_s, tid);
+                // restage this layer's block (after every warp left the previous layer's epilogue, which
+                // reads its bias row); it joins the pending (next-tile) group, so drain everything
+                if (li > 0) __syncthreads();
+                stage_weights_async(p, li, w_l, tid);
+                cp_async_commit();
+                cp_async_wait<0>();
                 __syncthreads();
             } else if (li > 0) {
                 __syncthreads();  // H_l written by the previous layer's epilogue
             }
-            const int fi_pad = pad8(L.f_in), fo_pad = pad8(L.f_out);
-            const int nchunks = fi_pad >> 3, nnt = fo_pad >> 3;
 
-            float acc[MT][4][4];
+            const int mslot = warp & (FWD_MSLOTS - 1), nt0 = (warp / FWD_MSLOTS) * 2;
+            const bool has_n = nt0 < nnt;  // this warp's n-tile half exists for this layer
+            float acc[MT][2][4];
 #pragma unroll
             for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int n = 0; n < 4; ++n)
+                for (int n = 0; n < 2; ++n)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
 
             uint32_t tk = bx, tprev = bs;  // T_k, and the buffer T_{k+1} is written to (holds T_{k-1})
             for (int k = 0; k < L.K; ++k) {
-                const uint32_t w_k = w_l + (uint32_t)(k * fo_pad) * 128u;
-                if (k + 1 < L.K) {
-                    if (STAGED) spmm_walk<HAS_VALS>(tk, tprev, k == 0, rb, re, rp_s, nz0, pre_a, val_a, key);
+                const uint32_t whi_k = w_l + (uint32_t)(k * fo_pad) * 128u;
+                const uint32_t wlo_k = whi_k + (uint32_t)w_rows_l * 128u;
+                const bool more = (k + 1 < L.K) && !(p.debug & 1);
+                HeadState hs;
+                hs.pending = 0;
+                if (more) {
+                    if (STAGED) spmm_seg_walk<HAS_VALS>(tk, tprev, k == 0, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
                     else spmm_rows_global<HAS_VALS>(tk, tprev, k == 0, rows, rp_s, p.b.colidx, p.b.vals, node0, warp, key);
                 }
+                // the dense contribution of T_k right behind the walk: warps that finish their segment early
+                // start on the tensor cores, so one barrier absorbs the imbalance of both
+                if (has_n && !(p.debug & 2)) {
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const int mt = warp + m * MHO_NWARPS;
-                    if (mt < n_mtiles) mma_tile(acc[m], tk, mt * 16, w_k, nchunks, nnt, lane);
+                    for (int m = 0; m < MT; ++m) {
+                        const int mt = mslot + m * FWD_MSLOTS;
+                        if (mt < n_mtiles) mma_tile(acc[m], tk, mt * 16, whi_k, wlo_k, nchunks, nt0, nnt, lane);
+                    }
+                }
+                if (more && STAGED) {
+                    __syncthreads();  // every group's leftover is published
+                    spmm_fixup(tprev, k == 0, sg, group, rp_s, nz0, ckey, left_base, hs);
                 }
                 __syncthreads();
                 const uint32_t tmp = tk; tk = tprev; tprev = tmp;
@@ -347,12 +477,12 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
             const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const int mt = warp + m * MHO_NWARPS;
-                if (mt < n_mtiles) {
+                const int mt = mslot + m * FWD_MSLOTS;
+                if (has_n && mt < n_mtiles) {
 #pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        if (n < nnt) {
-                            const int col = n * 8 + 2 * t4;
+                    for (int n = 0; n < 2; ++n) {
+                        if (nt0 + n < nnt) {
+                            const int col = (nt0 + n) * 8 + 2 * t4;
                             const float b0 = bias_s[col], b1 = bias_s[col + 1];
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
@@ -396,8 +526,8 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 // -------------------------------------------------------------------------------------------
 // host launcher
 // -------------------------------------------------------------------------------------------
-static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, int n_bias, bool has_vals, bool prefetch) {
-    size_t s = (size_t)rows_cap * 128 * (prefetch ? 3 : 2) + (size_t)w_rows * 128 + (size_t)n_bias * 128;
+static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, bool has_vals, bool prefetch) {
+    size_t s = (size_t)rows_cap * 128 * (prefetch ? 3 : 2) + (size_t)w_rows * 128 + 4 * FWD_NWARPS * 128;
     const size_t csr_words = (size_t)((rows_cap + 2 + 3) & ~3) + (size_t)nnz_cap * (has_vals ? 2 : 1);
     s += csr_words * 4 * (prefetch ? 2 : 1);
     return s + 16;
@@ -415,7 +545,7 @@ static cudaError_t launch_one(const FwdParams& p, int grid, size_t smem, cudaStr
         if (e != cudaSuccess) return e;
         smem_set[dev & 63] = (int)smem;
     }
-    kern<<<grid, MHO_THREADS, smem, st>>>(p);
+    kern<<<grid, FWD_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -431,29 +561,28 @@ cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nn
     *too_large = false;
     p.rows_cap = pad16(max_tile_rows < 16 ? 16 : max_tile_rows);
     const bool has_vals = p.b.vals != nullptr;
-    const int MTn = (p.rows_cap + 16 * MHO_NWARPS - 1) / (16 * MHO_NWARPS);
+    const int MTn = (p.rows_cap + 16 * FWD_MSLOTS - 1) / (16 * FWD_MSLOTS);
     if (MTn > 4) { *too_large = true; return cudaSuccess; }
     const int mt_sel = MTn <= 1 ? 1 : (MTn <= 2 ? 2 : 4);
-    const int reg_limit = mt_sel == 1 ? 3 : (mt_sel == 2 ? 2 : 1);
+    const int reg_limit = mt_sel == 1 ? 2 : 1;
 
-    // weight images: keep every layer resident when that costs <= 48 KB, else restage per layer
+    // weight blocks (hi + lo images + bias row per layer): resident when all of them cost <= 64 KB
     int w_sum = 0, w_max = 0;
     for (int l = 0; l < p.n_layers; ++l) {
-        const int r = p.layers[l].K * pad8(p.layers[l].f_out);
+        const int r = wprep_layer_rows(p.layers[l].K, p.layers[l].f_out);
         p.w_row_off[l] = w_sum;
         w_sum += r;
         w_max = r > w_max ? r : w_max;
     }
-    p.w_resident = (p.n_layers == 1 || w_sum * 128 <= 48 * 1024) ? 1 : 0;
+    p.w_resident = (p.n_layers == 1 || w_sum * 128 <= 64 * 1024) ? 1 : 0;
     p.w_rows_cap = p.w_resident ? w_sum : w_max;
     if (!p.w_resident) for (int l = 0; l < p.n_layers; ++l) p.w_row_off[l] = 0;
-    const int n_bias = p.w_resident ? p.n_layers : 1;
 
     // preference order: staged+prefetch with >=2 CTAs/SM, staged+prefetch, staged, global CSR
     const int nnz_cap = (max_tile_nnz + 3) & ~3;
     bool staged = true, prefetch = true;
-    size_t smem = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, n_bias, has_vals, true);
-    const size_t smem_np = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, n_bias, has_vals, false);
+    size_t smem = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, true);
+    const size_t smem_np = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, false);
     auto per_sm_of = [&](size_t s) { int v = (int)((size_t)(228 * 1024) / (s + 1024)); return v > reg_limit ? reg_limit : v; };
     if (smem > (size_t)max_smem_optin || (per_sm_of(smem) < 2 && per_sm_of(smem_np) >= 2 && reg_limit >= 2)) {
         prefetch = false;
@@ -461,11 +590,17 @@ cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nn
     }
     if (smem > (size_t)max_smem_optin) {
         staged = false;
-        smem = fwd_smem_bytes(p.rows_cap, 0, p.w_rows_cap, n_bias, has_vals, false);
+        smem = fwd_smem_bytes(p.rows_cap, 0, p.w_rows_cap, has_vals, false);
         if (smem > (size_t)max_smem_optin) { *too_large = true; return cudaSuccess; }
     }
     p.nnz_cap = staged ? nnz_cap : 0;
     p.prefetch = prefetch ? 1 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.debug = dbg;
+        if (dbg & 8) { p.prefetch = 0; smem = smem_np; }
+    }
     int per_sm = per_sm_of(smem);
     if (per_sm < 1) per_sm = 1;
     int grid = num_sms * per_sm;

@@ -56,11 +56,43 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     if (!c) return MHO_OK;
     cudaSetDevice(c->device);
     for (auto& s : c->scratch) if (s.ptr) cudaFree(s.ptr);
+    if (c->wprep) cudaFree(c->wprep);
     delete c;
     return MHO_OK;
 }
 
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
+
+extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
+    if (c) c->wprep_valid = false;
+    return MHO_OK;
+}
+
+// (Re)build the packed TF32 hi/lo weight images when the layer set or the weights changed.
+static int ensure_prepared(mho_ctx* c, const mho_layer_t* layers, int n_layers, const LayerDev* ld, cudaStream_t st) {
+    bool same = c->wprep_valid && (int)c->wkey.size() == n_layers;
+    for (int l = 0; same && l < n_layers; ++l) {
+        mho_wkey k{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out};
+        same = (k == c->wkey[l]);
+    }
+    if (same) return MHO_OK;
+    int rows = 0;
+    for (int l = 0; l < n_layers; ++l) { c->wprep_row_off[l] = rows; rows += wprep_layer_rows(layers[l].K, layers[l].f_out); }
+    const size_t bytes = (size_t)rows * 128;
+    if (bytes > c->wprep_bytes) {
+        if (c->wprep) cudaFree(c->wprep);
+        c->wprep = nullptr; c->wprep_bytes = 0;
+        if (cudaMalloc((void**)&c->wprep, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
+        c->wprep_bytes = bytes;
+    }
+    cudaError_t e = prepare_weights_launch(ld, n_layers, c->wprep_row_off, c->wprep, st);
+    if (e != cudaSuccess) { mho_set_error("prepare_weights launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    c->wkey.clear();
+    for (int l = 0; l < n_layers; ++l) c->wkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
+    c->wprep_valid = true;
+    return MHO_OK;
+}
 
 // grow-only device scratch slots (used by the *_host convenience calls and the backward reducer)
 void* mho_scratch(mho_ctx* c, int slot, size_t bytes) {
@@ -105,6 +137,17 @@ extern "C" int mho_plan_tiles(const int32_t* goff, const int32_t* rowptr, int32_
     *n_tiles = nt;
     *max_rows = mr;
     *max_nnz = mz;
+    return MHO_OK;
+}
+
+extern "C" int mho_fill_tile_info(const int32_t* goff, const int32_t* rowptr, const int32_t* tile_off, int32_t n_tiles,
+                                  int32_t* out) {
+    if (!goff || !rowptr || !out || n_tiles < 0) { mho_set_error("mho_fill_tile_info: invalid argument"); return MHO_ERR_INVALID; }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int g0 = tile_off ? tile_off[t] : t, g1 = tile_off ? tile_off[t + 1] : t + 1;
+        const int n0 = goff[g0], n1 = goff[g1];
+        out[4 * t + 0] = n0; out[4 * t + 1] = n1 - n0; out[4 * t + 2] = rowptr[n0]; out[4 * t + 3] = rowptr[n1] - rowptr[n0];
+    }
     return MHO_OK;
 }
 
@@ -171,10 +214,15 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     memset(&p, 0, sizeof(p));
     p.b.graph_off = b->graph_off; p.b.rowptr = b->rowptr; p.b.colidx = b->colidx; p.b.vals = b->vals;
     p.b.tile_off = b->tile_off; p.b.n_graphs = b->n_graphs;
+    p.b.tile_info = b->tile_info;
     p.b.n_tiles = b->tile_off ? b->n_tiles : b->n_graphs;
     p.n_layers = n_layers;
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);
     p.X = X; p.Y = Y; p.saved = (float*)saved; p.total_nodes = b->total_nodes;
+    rc = ensure_prepared(c, layers, n_layers, p.layers, (cudaStream_t)stream);
+    if (rc) return rc;
+    p.wprep = c->wprep;
+    for (int l = 0; l < n_layers; ++l) p.wprep_row_off[l] = c->wprep_row_off[l];
     bool too_large = false;
     cudaError_t e = cheb_forward_launch(p, b->max_tile_rows, b->max_tile_nnz, c->num_sms, c->max_smem_optin,
                                         (cudaStream_t)stream, &too_large);
@@ -209,7 +257,11 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
     if (rc) return rc;
     const int f_in = layers[0].f_in, f_out = layers[n_layers - 1].f_out;
     const size_t b_goff = (size_t)(n_graphs + 1) * 4, b_rp = (size_t)(total_nodes + 1) * 4, b_ci = (size_t)nnz * 4;
-    const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_to = (size_t)(n_tiles + 1) * 4;
+    const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_to = (size_t)(n_tiles + 1) * 4 + (size_t)n_tiles * 16 + 16;
+    std::vector<int32_t> tile_blob((size_t)(n_tiles + 1) + 4 + (size_t)n_tiles * 4);
+    const size_t ti_off = ((size_t)(n_tiles + 1) + 3) & ~(size_t)3;  // 16 B aligned start of tile_info inside the blob
+    memcpy(tile_blob.data(), tile_off.data(), (size_t)(n_tiles + 1) * 4);
+    mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tile_blob.data() + ti_off);
     const size_t b_x = (size_t)total_nodes * f_in * 4, b_y = (size_t)total_nodes * f_out * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total = al(b_goff) + al(b_rp) + al(b_ci) + al(b_va) + al(b_to) + al(b_x) + al(b_y);
@@ -228,13 +280,13 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
     if (nnz) CUDA_TRY(cudaMemcpyAsync(d_ci, colidx_h, b_ci, cudaMemcpyHostToDevice, st));
     if (vals_h && nnz) CUDA_TRY(cudaMemcpyAsync(d_va, vals_h, b_va, cudaMemcpyHostToDevice, st));
     // tile_off lives in a std::vector that dies at return: stage it synchronously-safe via a pageable copy
-    CUDA_TRY(cudaMemcpyAsync(d_to, tile_off.data(), b_to, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_to, tile_blob.data(), (ti_off + (size_t)n_tiles * 4) * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_x, X_h, b_x, cudaMemcpyHostToDevice, st));
     mho_batch_t b;
     memset(&b, 0, sizeof(b));
     b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
     b.graph_off = d_goff; b.rowptr = d_rp; b.colidx = d_ci; b.vals = d_va;
-    b.tile_off = d_to; b.n_tiles = n_tiles; b.max_tile_rows = mr; b.max_tile_nnz = mz;
+    b.tile_off = d_to; b.tile_info = d_to + ti_off; b.n_tiles = n_tiles; b.max_tile_rows = mr; b.max_tile_nnz = mz;
     rc = mho_cheb_forward(c, &b, layers, n_layers, d_x, d_y, nullptr, stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(Y_h, d_y, b_y, cudaMemcpyDeviceToHost, st));

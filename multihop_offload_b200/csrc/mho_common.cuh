@@ -67,6 +67,20 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     hi = f2tf32(x);
     lo = f2tf32(x - __uint_as_float(hi));
 }
+// Cheap round-to-nearest(ties away) TF32 split with integer ops (the PTX cvt.rna.tf32.f32 expands to
+// ~5 instructions with its inf/nan handling): hi = rn_tf32(x), lo = rn_tf32(x - hi).  5 instructions.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+__device__ __forceinline__ float4 lds_f128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -161,6 +175,7 @@ struct BatchDev {
     const int32_t* colidx;
     const float* vals;
     const int32_t* tile_off;
+    const int32_t* tile_info;  // optional [n_tiles][4] = {node0, rows, nz0, nnz}
     int n_tiles;
     int n_graphs;
 };
@@ -172,11 +187,15 @@ struct FwdParams {
     const float* X;
     float* Y;
     float* saved;     // nullable
+    // prepared weights (mho_prepare kernel): per layer [hi image][lo image][bias(32)] as 128 B rows
+    const unsigned char* wprep;
+    int wprep_row_off[MHO_MAX_LAYERS];  // first 128 B row of each layer's block inside wprep
     int rows_cap;     // multiple of 16, >= max tile rows
     int nnz_cap;      // staged nnz capacity (multiple of 4); 0 => read CSR from global memory
-    int w_rows_cap;   // rows (of 128 B) of the fp32 W image region
-    int w_resident;   // 1: every layer's image stays in smem for the CTA's lifetime; 0: restaged per layer per tile
-    int w_row_off[MHO_MAX_LAYERS];  // first image row of each layer (w_resident) else 0
+    int w_rows_cap;   // rows (of 128 B) of the smem weight region (hi+lo images)
+    int w_resident;   // 1: every layer's images stay in smem for the CTA's lifetime; 0: restaged per layer per tile
+    int w_row_off[MHO_MAX_LAYERS];  // first smem image row of each layer (w_resident) else 0
     int prefetch;     // 1: third tile buffer + second CSR staging set, next tile fetched with cp.async
     int total_nodes;
+    int debug;        // MHO_DEBUG env (perf experiments only): 1 skip sparse step, 2 skip mma, 8 no prefetch
 };

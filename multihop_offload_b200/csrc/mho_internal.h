@@ -11,7 +11,18 @@ struct mho_scratch_slot {
     size_t bytes = 0;
 };
 
+struct mho_wkey {
+    const void* W; const void* b; int K, f_in, f_out;
+    bool operator==(const mho_wkey& o) const { return W == o.W && b == o.b && K == o.K && f_in == o.f_in && f_out == o.f_out; }
+};
+
 struct mho_ctx {
+    // prepared-weight cache (see mho_invalidate_weights)
+    std::vector<mho_wkey> wkey;
+    bool wprep_valid = false;
+    unsigned char* wprep = nullptr;
+    size_t wprep_bytes = 0;
+    int wprep_row_off[MHO_MAX_LAYERS] = {0};
     int device = 0;
     int num_sms = 0;
     int max_smem_optin = 0;
@@ -25,5 +36,8 @@ void* mho_scratch(mho_ctx* c, int slot, size_t bytes);
 struct LayerDev;
 struct FwdParams;
 void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, LayerDev* out);
+int wprep_layer_rows(int K, int f_out);
+cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const int* row_off, unsigned char* out,
+                                   cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
                                 cudaStream_t st, bool* too_large);

@@ -33,6 +33,7 @@ class KerasAdamReplay:
         assert flat64.size == self.net.n_params
         self.master.copy_(torch.from_numpy(flat64))
         self.net.params.copy_(self.master.to(torch.float32))
+        self.net.weights_changed()
 
     def get_master(self):
         return self.master.detach().cpu().numpy().copy()

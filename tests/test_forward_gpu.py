@@ -166,7 +166,9 @@ def test_full_size_linearity_property(torch_cuda):
     off = batch.graph_off
     idx = np.concatenate([np.arange(off[i], off[i + 1]) for i in perm])
     Yp = net.forward(batch_p, X1[torch_cuda.from_numpy(idx).cuda()].contiguous())
-    assert torch_cuda.equal(Yp, Y1[torch_cuda.from_numpy(idx).cuda()])
+    # (not bit-equal: hub rows that straddle stream segments are summed in a position-dependent order)
+    Yref = Y1[torch_cuda.from_numpy(idx).cuda()]
+    assert (Yp - Yref).abs().max().item() <= 2e-5 * Yref.abs().max().item()
     # and a sample of graphs against the oracle at full batch size
     Xh = X1.cpu().numpy().astype(np.float64)
     for gi in rng.choice(len(mats), size=16, replace=False):
