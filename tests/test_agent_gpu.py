@@ -1,0 +1,109 @@
+"""GPU: the drop-in ACOAgent on libmho - forward (lambda -> delay matrices) and the :448 VJP against the
+committed goldens (shipped checkpoint x shipped networks).  The reference simulator is not available on
+the GPU box, so obj/env are rebuilt from the golden fixtures (fields of offloading_v3.py:284-333)."""
+import glob
+import os
+import sys
+import types
+
+import networkx as nx
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def stub_case(z):
+    n = z["X"].shape[0]
+    A = sp.csr_matrix((z["vals"], z["colidx"], z["rowptr"]), shape=(n, n))
+    obj = types.SimpleNamespace()
+    obj.gi_ext = nx.from_scipy_sparse_array(A)
+    obj.num_edges_ext = n
+    obj.edge_self_loop, obj.edge_rate_ext = z["X"][:, 0], z["X"][:, 1]
+    obj.jobs_arrivals, obj.edge_as_server = z["X"][:, 2], z["X"][:, 3]
+    obj.maps_ol_el, obj.maps_on_el = z["maps_ol_el"], z["maps_on_el"]
+    env = types.SimpleNamespace()
+    env.num_nodes, env.T = int(z["num_nodes"]), int(z["T"])
+    env.link_rates, env.cf_degs, env.proc_bws = z["link_rates"], z["cf_degs"], z["proc_bws"]
+    L = len(z["link_rates"])
+    env.num_links = L
+    env.adj_i = sp.csr_matrix((z["adj_i_vals"], z["adj_i_colidx"], z["adj_i_rowptr"]), shape=(L, L))
+    env.link_matrix = z["link_matrix"]
+    g = nx.Graph()
+    g.add_nodes_from(range(env.num_nodes))
+    g.add_edges_from([tuple(e) for e in z["edges"]])
+    env.graph_c = g
+    return obj, env
+
+
+@pytest.fixture()
+def agent(golden_dir, monkeypatch):
+    monkeypatch.setattr(sys, "argv", ["test"])
+    from multihop_offload_b200.gnn_offloading_agent import ACOAgent, FLAGS
+    FLAGS.device = "cuda:0"
+    FLAGS.K = 1
+    FLAGS.fix_diag = False
+    a = ACOAgent(FLAGS, 100)
+    a.load(os.path.join(golden_dir, "ckpt_BAT800"))
+    return a
+
+
+def test_forward_matches_golden_delay_matrices(agent, golden_dir):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz"))):
+        z = np.load(f)
+        obj, env = stub_case(z)
+        state, D_ts, D_np = agent.forward(obj, env)
+        lam = agent.predict(state).cpu().numpy()
+        assert np.abs(lam - z["lam"]).max() <= 1e-5 * np.abs(z["lam"]).max()
+        # numpy twin (bug-compatible wrapped diagonal) and TF tensor twin (relays = +inf)
+        gold = z["delay_mtx_bug"]
+        assert np.array_equal(np.isnan(D_np), np.isnan(gold))
+        m = ~np.isnan(gold)
+        assert np.abs(D_np[m] - gold[m]).max() <= 2e-5 * np.abs(gold[m]).max()
+        Dt = D_ts.cpu().numpy()
+        gt = np.nan_to_num(z["delay_mtx_ts"], nan=0.0, posinf=np.inf)
+        fin = np.isfinite(gt)
+        assert np.array_equal(np.isinf(Dt), np.isinf(gt))
+        assert np.abs(Dt[fin] - gt[fin]).max() <= 2e-5 * np.abs(gt[fin]).max()
+
+
+def test_vjp_from_grad_dist_matches_golden(agent, golden_dir):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz"))):
+        z = np.load(f)
+        obj, env = stub_case(z)
+        agent.forward(obj, env, save=True)
+        g = agent.vjp_from_grad_dist(z["grad_dist"]).cpu().numpy()
+        want = z["grad_flat"]
+        err = np.abs(g - want).max() / np.abs(want).max()
+        assert err < 5e-5, (os.path.basename(f), err)
+
+
+def test_predict_batch_equals_single_calls(agent, golden_dir):
+    states = []
+    for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz"))):
+        z = np.load(f)
+        obj, env = stub_case(z)
+        states.append(agent.makestate(nx.adjacency_matrix(obj.gi_ext), z["X"]))
+    outs = agent.predict_batch(states)
+    for s, y in zip(states, outs):
+        y1 = agent.predict(s)
+        assert (y - y1).abs().max().item() <= 1e-6 * max(y1.abs().max().item(), 1e-30)
+
+
+def test_replay_and_checkpoint_roundtrip_on_device(agent, tmp_path):
+    import torch
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        agent.memorize(torch.as_tensor(rng.normal(size=agent.net.n_params).astype(np.float32)).cuda(), float(i), 0.0)
+    w0 = agent.optimizer.get_master()
+    loss = agent.replay(4)
+    assert np.isfinite(loss) and agent.optimizer.iterations == 4
+    w1 = agent.optimizer.get_master()
+    assert np.abs(w1 - w0).max() > 0
+    np.testing.assert_array_equal(agent.net.get_flat().astype(np.float32), w1.astype(np.float32))
+    agent.save(str(tmp_path / "m" / "cp-0001.ckpt"))
+    from multihop_offload_b200 import tf_bundle
+    back = tf_bundle.load_weights(tf_bundle.latest_checkpoint(str(tmp_path / "m")))
+    flat = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for W, b in back])
+    np.testing.assert_array_equal(flat, w1)   # fp64 master weights survive bit for bit
