@@ -64,8 +64,10 @@ typedef struct {
     /* tile plan (from mho_plan_tiles): tile t = graphs [tile_off[t], tile_off[t+1]) processed
        by one CTA; NULL => one graph per tile */
     const int32_t* tile_off;   /* [n_tiles+1] graph indices, device */
-    const int32_t* tile_info;  /* optional [n_tiles][4] = {node0, rows, nz0, nnz} (device, 16 B aligned):
-                                  saves the kernel three dependent loads per tile; NULL => derived */
+    const int32_t* tile_info;  /* optional [n_tiles][4] = {node0, rows, nz0, nnz} (device, 16 B aligned), in ANY
+                                  order: with it the forward kernel's CTAs pull tiles dynamically in the listed
+                                  order (list the largest first) instead of a static round-robin over tile_off;
+                                  NULL => bounds derived from tile_off/graph_off/rowptr, static schedule */
     int32_t n_tiles;
     int32_t max_tile_rows;     /* max over tiles of the node count (host-known) */
     int32_t max_tile_nnz;      /* max over tiles of the nnz count (host-known) */

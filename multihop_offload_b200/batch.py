@@ -93,6 +93,10 @@ class GraphBatch:
                                           self.n_tiles, self.tile_info.ctypes.data), "mho_fill_tile_info")
         _lib.check(lib.mho_fill_tile_info(self.graph_off.ctypes.data, self.rowptr.ctypes.data, None,
                                           self.n_graphs, self.graph_info.ctypes.data), "mho_fill_tile_info")
+        # largest tile first: the kernel's CTAs pull tiles in this order from a global counter
+        if self.n_tiles > 1:
+            cost = 3 * self.tile_info[:, 1].astype(np.int64) + self.tile_info[:, 3]
+            self.tile_info = np.ascontiguousarray(self.tile_info[np.argsort(-cost, kind="stable")])
         # one-graph-per-tile statistics (the backward runs one graph per CTA)
         if self.n_graphs:
             sizes = np.diff(self.graph_off)

@@ -173,25 +173,39 @@ struct HeadState {
     int pending;    // 1: the head row's sum is still in `head` and must be completed by spmm_fixup
 };
 
-__device__ __forceinline__ void emit_row(uint32_t Tdst, int row, uint32_t ckey, bool first, const float4& acc) {
+template <bool FIRST>
+__device__ __forceinline__ void emit_row(uint32_t Tdst, int row, uint32_t ckey, const float4& acc) {
     const uint32_t d = Tdst + (swz_row((uint32_t)row) ^ ckey);
-    float4 o = acc;
-    if (!first) {
+    if (FIRST) {
+        sts_f128(d, acc);
+    } else {
         const float4 q = lds_f128(d);
-        o = make_float4(2.f * acc.x - q.x, 2.f * acc.y - q.y, 2.f * acc.z - q.z, 2.f * acc.w - q.w);
+        sts_f128(d, make_float4(fmaf(2.f, acc.x, -q.x), fmaf(2.f, acc.y, -q.y), fmaf(2.f, acc.z, -q.z), fmaf(2.f, acc.w, -q.w)));
     }
-    sts_f128(d, o);
 }
 
-__device__ __forceinline__ void emit_empty_rows(uint32_t Tdst, int& row, int rows, const int* rp_s, uint32_t ckey, bool first) {
+template <bool FIRST>
+__device__ __noinline__ void emit_empty_rows(uint32_t Tdst, int& row, int rows, const int* rp_s, uint32_t ckey) {
     while (row < rows && rp_s[row + 1] == rp_s[row]) {
-        emit_row(Tdst, row, ckey, first, make_float4(0.f, 0.f, 0.f, 0.f));
+        emit_row<FIRST>(Tdst, row, ckey, make_float4(0.f, 0.f, 0.f, 0.f));
         ++row;
     }
 }
 
+// one stream entry: gather, accumulate
 template <bool HAS_VALS>
-__device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, bool first, const SegInfo& sg, int rows,
+__device__ __forceinline__ void gather_acc(float4& acc, uint32_t Tsrc, uint32_t cur, float cv, uint32_t ckey) {
+    const float4 t = lds_f128(Tsrc + ((cur & ~3u) ^ ckey));
+    if (HAS_VALS) {
+        acc.x = fmaf(cv, t.x, acc.x); acc.y = fmaf(cv, t.y, acc.y);
+        acc.z = fmaf(cv, t.z, acc.z); acc.w = fmaf(cv, t.w, acc.w);
+    } else {
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+}
+
+template <bool HAS_VALS, bool FIRST>
+__device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, const SegInfo& sg, int rows,
                                               const int* rp_s, uint32_t pre_a, uint32_t val_a, uint32_t ckey,
                                               uint32_t left_a, bool is_group0, HeadState& hs) {
     hs.pending = 0;
@@ -199,40 +213,48 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, bool
     hs.head = make_float4(0.f, 0.f, 0.f, 0.f);
     if (is_group0) {  // empty rows in front of the first stored entry belong to nobody's stream
         int r = 0;
-        emit_empty_rows(Tdst, r, rows, rp_s, ckey, first);
+        emit_empty_rows<FIRST>(Tdst, r, rows, rp_s, ckey);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sg.n > 0) {
         int row = sg.r0;
-        int waiting = sg.mid;  // the first row end seen closes a row that started in an earlier segment
         uint32_t ea = pre_a + (uint32_t)sg.sb * 4u, va = val_a + (uint32_t)sg.sb * 4u;
+        const uint32_t ea_end = ea + (uint32_t)sg.n * 4u;
         uint32_t pw = lds_u32(ea);
         float vv = HAS_VALS ? lds_f32(va) : 1.f;
-        for (int s = 0; s < sg.n; ++s) {
+        // the first row end seen by a segment that starts mid-row closes a row begun in an earlier segment:
+        // its partial sum is parked (completed by spmm_fixup), peeled out of the steady-state loop
+        if (sg.mid) {
+            for (;;) {
+                const uint32_t cur = pw;
+                const float cv = vv;
+                ea += 4; va += 4;
+                if (ea < ea_end) { pw = lds_u32(ea); if (HAS_VALS) vv = lds_f32(va); }
+                gather_acc<HAS_VALS>(acc, Tsrc, cur, cv, ckey);
+                if (cur & 1u) {
+                    hs.head = acc; hs.head_row = row; hs.pending = 1;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ++row;
+                    if (cur & 2u) emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
+                    break;
+                }
+                if (ea >= ea_end) break;
+            }
+        }
+        while (ea < ea_end) {
             const uint32_t cur = pw;
             const float cv = vv;
             ea += 4; va += 4;
-            if (s + 1 < sg.n) {  // next step's stream word is in flight during the gather
+            if (ea < ea_end) {  // next step's stream word is in flight during the gather
                 pw = lds_u32(ea);
                 if (HAS_VALS) vv = lds_f32(va);
             }
-            const float4 t = lds_f128(Tsrc + ((cur & ~3u) ^ ckey));
-            if (HAS_VALS) {
-                acc.x = fmaf(cv, t.x, acc.x); acc.y = fmaf(cv, t.y, acc.y);
-                acc.z = fmaf(cv, t.z, acc.z); acc.w = fmaf(cv, t.w, acc.w);
-            } else {
-                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
+            gather_acc<HAS_VALS>(acc, Tsrc, cur, cv, ckey);
             if (cur & 1u) {
-                if (waiting) {
-                    hs.head = acc; hs.head_row = row; hs.pending = 1;
-                    waiting = 0;
-                } else {
-                    emit_row(Tdst, row, ckey, first, acc);
-                }
+                emit_row<FIRST>(Tdst, row, ckey, acc);
                 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 ++row;
-                if (cur & 2u) emit_empty_rows(Tdst, row, rows, rp_s, ckey, first);
+                if (cur & 2u) emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
             }
         }
     }
@@ -240,17 +262,20 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, bool
 }
 
 // after a barrier: complete the rows that straddled segment boundaries (deterministic order)
-__device__ __forceinline__ void spmm_fixup(uint32_t Tdst, bool first, const SegInfo& sg, int group, const int* rp_s, int nz0,
+template <bool FIRST>
+__device__ __forceinline__ void spmm_fixup(uint32_t Tdst, const SegInfo& sg, int group, const int* rp_s, int nz0,
                                            uint32_t ckey, uint32_t left_base, const HeadState& hs) {
     if (hs.pending) {
-        const int j0 = (rp_s[hs.head_row] - nz0) / sg.seg_len;  // group holding the row's first entry
+        const int e_start = rp_s[hs.head_row] - nz0;  // the row's first entry lives in group j0 <= group - 1
+        int j0 = group - 1;
+        while (j0 > 0 && j0 * sg.seg_len > e_start) --j0;
         float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = j0; j < group; ++j) {
             const float4 q = lds_f128(left_base + (uint32_t)j * 128u + ckey);
             tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
         }
         tot.x += hs.head.x; tot.y += hs.head.y; tot.z += hs.head.z; tot.w += hs.head.w;
-        emit_row(Tdst, hs.head_row, ckey, first, tot);
+        emit_row<FIRST>(Tdst, hs.head_row, ckey, tot);
     }
 }
 
@@ -342,30 +367,48 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     if (p.w_resident)
         for (int l = 0; l < p.n_layers; ++l) stage_weights_async(p, l, w_a + (uint32_t)p.w_row_off[l] * 128u, tid);
 
-    int tile = blockIdx.x;
-    if (tile >= p.b.n_tiles) { cp_async_wait<0>(); return; }
-    TileInfo cur = load_tile_info(p.b, tile);
+    // ---- tile scheduler.  Dynamic (largest tile first, CTAs pull indices from a global counter) when the
+    // batch carries tile_info - with only ~2 tiles per CTA a static split leaves 30 % of the SMs idle in
+    // the last round - else static round-robin.  The pipeline always knows the next TWO tile indices.
+    int* s_idx = csr0 + (p.prefetch ? 2 : 1) * csr_words;  // two ints behind the CSR staging set(s)
+    const bool dyn = (p.sched != nullptr);
+    int it = 0;
+    int i_cur, i_nxt;
+    if (dyn) {
+        if (tid == 0) { s_idx[0] = atomicAdd(p.sched, 1); s_idx[1] = atomicAdd(p.sched, 1); }
+        __syncthreads();
+        i_cur = s_idx[0]; i_nxt = s_idx[1];
+        __syncthreads();  // slot 0 is rewritten by thread 0 at the top of the first iteration
+    } else {
+        i_cur = blockIdx.x; i_nxt = blockIdx.x + gridDim.x;
+    }
+    auto finish = [&]() {
+        cp_async_wait<0>();
+        if (dyn && tid == 0) {  // the last CTA out re-arms the counters for the next launch
+            __threadfence();
+            if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+        }
+    };
+    if (i_cur >= p.b.n_tiles) { finish(); return; }
+    TileInfo cur = load_tile_info(p.b, i_cur);
     TileInfo nxt = cur;
-    bool has_nxt = (tile + (int)gridDim.x) < p.b.n_tiles;
+    bool has_nxt = i_nxt < p.b.n_tiles;
     if (p.prefetch) {
         issue_tile_loads<HAS_VALS, STAGED>(p, cur, bx, csr_a0, csr_a0 + rp_words * 4, csr_a0 + (rp_words + p.nnz_cap) * 4, tid);
         cp_async_commit();
-        if (has_nxt) nxt = load_tile_info(p.b, tile + gridDim.x);
     }
+    if (has_nxt) nxt = load_tile_info(p.b, i_nxt);
 
-    for (; tile < p.b.n_tiles; tile += gridDim.x) {
+    for (;; ++it) {
         const uint32_t rp_a = csr_a0 + (uint32_t)(cs * csr_words) * 4u;
         const uint32_t pre_a = rp_a + rp_words * 4, val_a = pre_a + p.nnz_cap * 4;
         const int* rp_s = csr0 + cs * csr_words;
-        TileInfo nn = nxt;
-        bool has_nn = false;
+        if (dyn && tid == 0) s_idx[it & 1] = has_nxt ? atomicAdd(p.sched, 1) : p.b.n_tiles;  // index of tile it+2
         if (p.prefetch) {
-            // next tile's loads go out now; the tile after that has its bounds fetched (consumed next iteration)
+            // next tile's loads go out now
             if (has_nxt) {
                 const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
                 issue_tile_loads<HAS_VALS, STAGED>(p, nxt, bp, rp_n, rp_n + rp_words * 4, rp_n + (rp_words + p.nnz_cap) * 4, tid);
-                has_nn = (tile + 2 * (int)gridDim.x) < p.b.n_tiles;
-                if (has_nn) nn = load_tile_info(p.b, tile + 2 * gridDim.x);
             }
             cp_async_commit();
             cp_async_wait<1>();  // the current tile's group has landed; the next tile's may still fly
@@ -375,6 +418,11 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
             cp_async_wait<0>();
         }
         __syncthreads();
+        // the tile after next: its index was published by the barrier, its bounds are consumed next iteration
+        const int i_nn = dyn ? s_idx[it & 1] : (int)(blockIdx.x + (it + 2) * gridDim.x);
+        const bool has_nn = has_nxt && i_nn < p.b.n_tiles;
+        TileInfo nn = nxt;
+        if (has_nn) nn = load_tile_info(p.b, i_nn);
 
         const int rows = cur.rows, node0 = cur.node0, nz0 = cur.nz0;
         const int n_mtiles = (rows + 15) >> 4;
@@ -450,7 +498,10 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                 HeadState hs;
                 hs.pending = 0;
                 if (more) {
-                    if (STAGED) spmm_seg_walk<HAS_VALS>(tk, tprev, k == 0, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
+                    if (STAGED) {
+                        if (k == 0) spmm_seg_walk<HAS_VALS, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
+                        else spmm_seg_walk<HAS_VALS, false>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
+                    }
                     else spmm_rows_global<HAS_VALS>(tk, tprev, k == 0, rows, rp_s, p.b.colidx, p.b.vals, node0, warp, key);
                 }
                 // the dense contribution of T_k right behind the walk: warps that finish their segment early
@@ -464,7 +515,8 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                 }
                 if (more && STAGED) {
                     __syncthreads();  // every group's leftover is published
-                    spmm_fixup(tprev, k == 0, sg, group, rp_s, nz0, ckey, left_base, hs);
+                    if (k == 0) spmm_fixup<true>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
+                    else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                 }
                 __syncthreads();
                 const uint32_t tmp = tk; tk = tprev; tprev = tmp;
@@ -510,17 +562,17 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
             }
         }
         // rotate: the prefetched buffer becomes the next tile's X, the old X/scratch become scratch/prefetch
+        if (!has_nxt) break;
         if (p.prefetch) {
             const uint32_t o_bx = bx, o_bs = bs;
             bx = bp; bs = o_bx; bp = o_bs;
             cs ^= 1;
-            cur = nxt; nxt = nn; has_nxt = has_nn;
         } else {
-            if (tile + (int)gridDim.x < p.b.n_tiles) cur = load_tile_info(p.b, tile + gridDim.x);
             __syncthreads();  // staging buffers are rewritten right away by the next tile's loads
         }
+        cur = nxt; nxt = nn; has_nxt = has_nn;
     }
-    cp_async_wait<0>();
+    finish();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -530,7 +582,7 @@ static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, bool has_val
     size_t s = (size_t)rows_cap * 128 * (prefetch ? 3 : 2) + (size_t)w_rows * 128 + 4 * FWD_NWARPS * 128;
     const size_t csr_words = (size_t)((rows_cap + 2 + 3) & ~3) + (size_t)nnz_cap * (has_vals ? 2 : 1);
     s += csr_words * 4 * (prefetch ? 2 : 1);
-    return s + 16;
+    return s + 16;  // + the scheduler's two index slots
 }
 
 template <int MT, bool HAS_VALS, bool STAGED>
@@ -595,6 +647,7 @@ cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nn
     }
     p.nnz_cap = staged ? nnz_cap : 0;
     p.prefetch = prefetch ? 1 : 0;
+    if (p.b.tile_info == nullptr) p.sched = nullptr;  // static round-robin without a (sorted) tile_info
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }

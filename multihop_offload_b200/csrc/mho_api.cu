@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "mho_common.cuh"
@@ -48,6 +49,11 @@ extern "C" int mho_create(mho_ctx_t** out, int device) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaMalloc((void**)&c->sched, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->sched, 0, 2 * sizeof(int)) != cudaSuccess) {
+        mho_set_error("mho_create: cudaMalloc for the scheduler state failed");
+        delete c;
+        return MHO_ERR_CUDA;
+    }
     *out = c;
     return MHO_OK;
 }
@@ -57,6 +63,11 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     cudaSetDevice(c->device);
     for (auto& s : c->scratch) if (s.ptr) cudaFree(s.ptr);
     if (c->wprep) cudaFree(c->wprep);
+    if (c->sched) cudaFree(c->sched);
+    if (c->h2d_stream) {
+        cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
+        for (int i = 0; i < 2 * MHO_MAX_CHUNKS + 1; ++i) cudaEventDestroy(c->ev[i]);
+    }
     delete c;
     return MHO_OK;
 }
@@ -222,6 +233,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     rc = ensure_prepared(c, layers, n_layers, p.layers, (cudaStream_t)stream);
     if (rc) return rc;
     p.wprep = c->wprep;
+    p.sched = c->sched;
     for (int l = 0; l < n_layers; ++l) p.wprep_row_off[l] = c->wprep_row_off[l];
     bool too_large = false;
     cudaError_t e = cheb_forward_launch(p, b->max_tile_rows, b->max_tile_nnz, c->num_sms, c->max_smem_optin,
@@ -239,6 +251,10 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
 // ---------------------------------------------------------------------------------------------
 // Host-buffer convenience: numpy in / numpy out, like ACOAgent.predict (gnn_offloading_agent.py:144-150)
 // ---------------------------------------------------------------------------------------------
+// The call is pipelined over chunks of the batch on three streams - uploads, kernels (the caller's stream),
+// downloads - so PCIe in, compute and PCIe out overlap; with pinned host buffers the step costs about
+// max(H2D, D2H) instead of their sum.  Global node / nnz offsets are kept (tile_info carries them), so a
+// chunk is just a slice of every array uploaded to its final place.
 extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
                                      const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
                                      int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream) {
@@ -251,45 +267,97 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
     const int total_nodes = goff_h[n_graphs];
     const int64_t nnz = rowptr_h[total_nodes];
     if (total_nodes == 0) return MHO_OK;
+    if (nnz > 0 && !colidx_h) { mho_set_error("mho_cheb_forward_host: colidx is NULL"); return MHO_ERR_INVALID; }
     std::vector<int32_t> tile_off((size_t)n_graphs + 1);
     int32_t n_tiles = 0, mr = 0, mz = 0;
     rc = mho_plan_tiles(goff_h, rowptr_h, n_graphs, 128, tile_off.data(), &n_tiles, &mr, &mz);
     if (rc) return rc;
+    std::vector<int32_t> tinfo((size_t)n_tiles * 4 + 4);
+    mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tinfo.data());
+
+    // chunks: contiguous runs of tiles of roughly equal bytes, at least ~192 tiles each, at most 8 chunks
+    int n_chunks = n_tiles / 192;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 8) n_chunks = 8;
+    std::vector<int> cstart((size_t)n_chunks + 1, 0);
+    {
+        const long long total_cost = 64LL * total_nodes + 2LL * nnz;
+        int t = 0;
+        for (int k = 1; k < n_chunks; ++k) {
+            const long long target = total_cost * k / n_chunks;
+            while (t < n_tiles && 64LL * tinfo[4 * t] + 2LL * tinfo[4 * t + 2] < target) ++t;
+            cstart[k] = t;
+        }
+        cstart[n_chunks] = n_tiles;
+    }
+    // inside every chunk: largest tile first for the kernel's dynamic scheduler (tinfo is consumed in order)
+    for (int k = 0; k < n_chunks; ++k) {
+        struct T4 { int32_t v[4]; };
+        T4* beg = reinterpret_cast<T4*>(tinfo.data()) + cstart[k];
+        T4* end = reinterpret_cast<T4*>(tinfo.data()) + cstart[k + 1];
+        // remember the chunk's extent before reordering
+        std::stable_sort(beg, end, [](const T4& a, const T4& b) { return 3LL * a.v[1] + a.v[3] > 3LL * b.v[1] + b.v[3]; });
+    }
+
     const int f_in = layers[0].f_in, f_out = layers[n_layers - 1].f_out;
-    const size_t b_goff = (size_t)(n_graphs + 1) * 4, b_rp = (size_t)(total_nodes + 1) * 4, b_ci = (size_t)nnz * 4;
-    const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_to = (size_t)(n_tiles + 1) * 4 + (size_t)n_tiles * 16 + 16;
-    std::vector<int32_t> tile_blob((size_t)(n_tiles + 1) + 4 + (size_t)n_tiles * 4);
-    const size_t ti_off = ((size_t)(n_tiles + 1) + 3) & ~(size_t)3;  // 16 B aligned start of tile_info inside the blob
-    memcpy(tile_blob.data(), tile_off.data(), (size_t)(n_tiles + 1) * 4);
-    mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tile_blob.data() + ti_off);
+    const size_t b_rp = (size_t)(total_nodes + 1) * 4, b_ci = (size_t)nnz * 4;
+    const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_ti = (size_t)n_tiles * 16 + 16;
     const size_t b_x = (size_t)total_nodes * f_in * 4, b_y = (size_t)total_nodes * f_out * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total = al(b_goff) + al(b_rp) + al(b_ci) + al(b_va) + al(b_to) + al(b_x) + al(b_y);
+    const size_t total = al(b_rp) + al(b_ci) + al(b_va) + al(b_ti) + al(b_x) + al(b_y);
     char* base = (char*)mho_scratch(c, 0, total);
     if (!base) { mho_set_error("mho_cheb_forward_host: cudaMalloc of %zu B failed", total); return MHO_ERR_CUDA; }
     char* q = base;
-    int32_t* d_goff = (int32_t*)q; q += al(b_goff);
     int32_t* d_rp = (int32_t*)q; q += al(b_rp);
     int32_t* d_ci = (int32_t*)q; q += al(b_ci);
     float* d_va = vals_h ? (float*)q : nullptr; q += al(b_va);
-    int32_t* d_to = (int32_t*)q; q += al(b_to);
+    int32_t* d_ti = (int32_t*)q; q += al(b_ti);
     float* d_x = (float*)q; q += al(b_x);
     float* d_y = (float*)q;
-    CUDA_TRY(cudaMemcpyAsync(d_goff, goff_h, b_goff, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_rp, rowptr_h, b_rp, cudaMemcpyHostToDevice, st));
-    if (nnz) CUDA_TRY(cudaMemcpyAsync(d_ci, colidx_h, b_ci, cudaMemcpyHostToDevice, st));
-    if (vals_h && nnz) CUDA_TRY(cudaMemcpyAsync(d_va, vals_h, b_va, cudaMemcpyHostToDevice, st));
-    // tile_off lives in a std::vector that dies at return: stage it synchronously-safe via a pageable copy
-    CUDA_TRY(cudaMemcpyAsync(d_to, tile_blob.data(), (ti_off + (size_t)n_tiles * 4) * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_x, X_h, b_x, cudaMemcpyHostToDevice, st));
-    mho_batch_t b;
-    memset(&b, 0, sizeof(b));
-    b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
-    b.graph_off = d_goff; b.rowptr = d_rp; b.colidx = d_ci; b.vals = d_va;
-    b.tile_off = d_to; b.tile_info = d_to + ti_off; b.n_tiles = n_tiles; b.max_tile_rows = mr; b.max_tile_nnz = mz;
-    rc = mho_cheb_forward(c, &b, layers, n_layers, d_x, d_y, nullptr, stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(Y_h, d_y, b_y, cudaMemcpyDeviceToHost, st));
+
+    if (!c->h2d_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * MHO_MAX_CHUNKS + 1; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    }
+    cudaStream_t sh = c->h2d_stream, sd = c->d2h_stream;
+    // uploads start once the caller's stream reaches this point (previous users of the scratch are done)
+    CUDA_TRY(cudaEventRecord(c->ev[2 * MHO_MAX_CHUNKS], st));
+    CUDA_TRY(cudaStreamWaitEvent(sh, c->ev[2 * MHO_MAX_CHUNKS], 0));
+    CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
+
+    // node / nnz extent of each chunk (tiles of a chunk are a contiguous run of graphs)
+    auto chunk_nodes = [&](int k, int& n0, int& n1) {
+        n0 = goff_h[tile_off[cstart[k]]]; n1 = goff_h[tile_off[cstart[k + 1]]];
+    };
+    for (int k = 0; k < n_chunks; ++k) {
+        int n0, n1;
+        chunk_nodes(k, n0, n1);
+        const int64_t z0 = rowptr_h[n0], z1 = rowptr_h[n1];
+        CUDA_TRY(cudaMemcpyAsync(d_rp + n0, rowptr_h + n0, (size_t)(n1 - n0 + 1) * 4, cudaMemcpyHostToDevice, sh));
+        if (z1 > z0) CUDA_TRY(cudaMemcpyAsync(d_ci + z0, colidx_h + z0, (size_t)(z1 - z0) * 4, cudaMemcpyHostToDevice, sh));
+        if (vals_h && z1 > z0) CUDA_TRY(cudaMemcpyAsync(d_va + z0, vals_h + z0, (size_t)(z1 - z0) * 4, cudaMemcpyHostToDevice, sh));
+        CUDA_TRY(cudaMemcpyAsync(d_x + (size_t)n0 * f_in, X_h + (size_t)n0 * f_in, (size_t)(n1 - n0) * f_in * 4, cudaMemcpyHostToDevice, sh));
+        CUDA_TRY(cudaEventRecord(c->ev[k], sh));
+
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev[k], 0));
+        mho_batch_t b;
+        memset(&b, 0, sizeof(b));
+        b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
+        b.graph_off = (const int32_t*)d_rp;  // never dereferenced: tile_info carries the bounds
+        b.rowptr = d_rp; b.colidx = d_ci; b.vals = d_va;
+        b.tile_off = (const int32_t*)d_ti;   // non-NULL marks "tiled"; bounds again come from tile_info
+        b.tile_info = d_ti + 4 * (size_t)cstart[k];
+        b.n_tiles = cstart[k + 1] - cstart[k]; b.max_tile_rows = mr; b.max_tile_nnz = mz;
+        if (b.n_tiles > 0) {
+            rc = mho_cheb_forward(c, &b, layers, n_layers, d_x, d_y, nullptr, stream);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev[MHO_MAX_CHUNKS + k], st));
+        CUDA_TRY(cudaStreamWaitEvent(sd, c->ev[MHO_MAX_CHUNKS + k], 0));
+        CUDA_TRY(cudaMemcpyAsync(Y_h + (size_t)n0 * f_out, d_y + (size_t)n0 * f_out, (size_t)(n1 - n0) * f_out * 4, cudaMemcpyDeviceToHost, sd));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd));
     CUDA_TRY(cudaStreamSynchronize(st));
     return MHO_OK;
 }

@@ -195,6 +195,7 @@ struct FwdParams {
     int w_rows_cap;   // rows (of 128 B) of the smem weight region (hi+lo images)
     int w_resident;   // 1: every layer's images stay in smem for the CTA's lifetime; 0: restaged per layer per tile
     int w_row_off[MHO_MAX_LAYERS];  // first smem image row of each layer (w_resident) else 0
+    int* sched;       // {next tile counter, finished-CTA counter} in device memory (dynamic scheduler) or NULL
     int prefetch;     // 1: third tile buffer + second CSR staging set, next tile fetched with cp.async
     int total_nodes;
     int debug;        // MHO_DEBUG env (perf experiments only): 1 skip sparse step, 2 skip mma, 8 no prefetch

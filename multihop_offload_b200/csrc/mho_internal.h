@@ -16,13 +16,19 @@ struct mho_wkey {
     bool operator==(const mho_wkey& o) const { return W == o.W && b == o.b && K == o.K && f_in == o.f_in && f_out == o.f_out; }
 };
 
+#define MHO_MAX_CHUNKS 8
+
 struct mho_ctx {
+    // pipelined host call: upload / download streams and per-chunk events
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev[2 * MHO_MAX_CHUNKS + 1] = {};
     // prepared-weight cache (see mho_invalidate_weights)
     std::vector<mho_wkey> wkey;
     bool wprep_valid = false;
     unsigned char* wprep = nullptr;
     size_t wprep_bytes = 0;
     int wprep_row_off[MHO_MAX_LAYERS] = {0};
+    int* sched = nullptr;  // two zero-initialised ints: dynamic tile scheduler state (self re-arming)
     int device = 0;
     int num_sms = 0;
     int max_smem_optin = 0;
