@@ -52,8 +52,10 @@ __device__ __forceinline__ TileInfo load_tile_info(const BatchDev& b, int tile) 
 
 // -------------------------------------------------------------------------------------------
 // Weight preparation (one tiny launch whenever the weights changed): Keras layout W[k][f][o] ->
-// per layer a block of 128 B rows  [hi image: K*fo_pad rows][lo image: K*fo_pad rows][bias: 1 row]
-// where image row (k*fo_pad + o) holds W[k][.][o] over f (transposed, 128B-swizzled on o) split into
+// per layer a block of 128 B rows  [hi image: K*fo_img rows][lo image: K*fo_img rows][bias: 8 rows],
+// fo_img = pad16(f_out) (the UMMA N extent), every image 1024 B aligned so that it is at once an
+// ldmatrix source and a tcgen05 SWIZZLE_128B K-major B operand;
+// image row (k*fo_img + o) holds W[k][.][o] over f (transposed, 128B-swizzled on o) split into
 // TF32 hi / lo parts (cvt.rna), so that a CTA stages it with straight 16 B cp.async copies and
 // ldmatrix yields ready-to-use mma B fragments.
 // -------------------------------------------------------------------------------------------
@@ -67,7 +69,7 @@ struct PrepParams {
 __global__ void prepare_weights_kernel(const __grid_constant__ PrepParams p) {
     for (int l = blockIdx.y; l < p.n_layers; l += gridDim.y) {
         const LayerDev& L = p.layers[l];
-        const int fo_pad = pad8(L.f_out);
+        const int fo_pad = pad16(L.f_out);
         const int n_rows = L.K * fo_pad;
         unsigned char* hi_img = p.out + (size_t)p.row_off[l] * 128;
         unsigned char* lo_img = hi_img + (size_t)n_rows * 128;
@@ -90,7 +92,7 @@ __global__ void prepare_weights_kernel(const __grid_constant__ PrepParams p) {
     }
 }
 
-int wprep_layer_rows(int K, int f_out) { return 2 * K * pad8(f_out) + 1; }
+int wprep_layer_rows(int K, int f_out) { return 2 * K * pad16(f_out) + 8; }
 
 cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const int* row_off, unsigned char* out,
                                    cudaStream_t st) {
@@ -105,7 +107,7 @@ cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const i
 
 // copy one layer's prepared block (hi, lo, bias) into shared memory with 16 B cp.async
 __device__ __forceinline__ void stage_weights_async(const FwdParams& p, int l, uint32_t dst, int tid) {
-    const int rows = 2 * p.layers[l].K * pad8(p.layers[l].f_out) + 1;
+    const int rows = 2 * p.layers[l].K * pad16(p.layers[l].f_out) + 8;
     const unsigned char* src = p.wprep + (size_t)p.wprep_row_off[l] * 128;
     for (int c = tid; c < rows * 8; c += FWD_THREADS) cp_async16(dst + (uint32_t)c * 16u, src + (size_t)c * 16);
 }
@@ -204,10 +206,10 @@ __device__ __forceinline__ void gather_acc(float4& acc, uint32_t Tsrc, uint32_t 
     }
 }
 
-template <bool HAS_VALS, bool FIRST>
+template <bool HAS_VALS, bool FIRST, bool WAIT_MMA>
 __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, const SegInfo& sg, int rows,
                                               const int* rp_s, uint32_t pre_a, uint32_t val_a, uint32_t ckey,
-                                              uint32_t left_a, bool is_group0, HeadState& hs) {
+                                              uint32_t left_a, bool is_group0, HeadState& hs, uint32_t mbar, uint32_t parity) {
     hs.pending = 0;
     hs.head_row = 0;
     hs.head = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -258,6 +260,7 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, cons
             }
         }
     }
+    if (WAIT_MMA) mbar_wait(mbar, parity);  // the slot aliases a tcgen05 operand tile: the step's MMAs must be done
     sts_f128(left_a, acc);  // partial sum of the row still open at the end of the segment (0 if none)
 }
 
@@ -336,7 +339,20 @@ __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileI
     }
 }
 
-template <int MT, bool HAS_VALS, bool STAGED>
+// split one [rows_cap][32] fp32 tile into TF32 hi / lo tiles (same swizzled layout): the tcgen05 A operands
+__device__ __forceinline__ void split_tile(uint32_t src, uint32_t ahi, uint32_t alo, int n_rows16, int tid) {
+    for (int idx = tid; idx < n_rows16 * 16 * 8; idx += FWD_THREADS) {
+        const uint32_t off = (uint32_t)idx << 4;  // (row, physical chunk) -> byte offset; the swizzle is a permutation
+        const float4 v = lds_f128(src + off);
+        uint32_t h[4], l[4];
+        split_tf32_fast(v.x, h[0], l[0]); split_tf32_fast(v.y, h[1], l[1]);
+        split_tf32_fast(v.z, h[2], l[2]); split_tf32_fast(v.w, h[3], l[3]);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ahi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]));
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(alo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]));
+    }
+}
+
+template <int MT, bool HAS_VALS, bool STAGED, bool TC5>
 __global__ void __launch_bounds__(FWD_THREADS, (MT == 1 ? 2 : 1))
 cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -347,9 +363,13 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     // ---- shared memory carve-up
     const uint32_t tile_bytes = (uint32_t)p.rows_cap * 128u;
     const int n_tbuf = p.prefetch ? 3 : 2;
-    unsigned char* Wimg = smem + (size_t)n_tbuf * tile_bytes;  // per layer: [hi rows][lo rows][bias row]
-    unsigned char* left_s = Wimg + (size_t)p.w_rows_cap * 128;  // 4*NWARPS leftover slots of 128 B
-    int* csr0 = reinterpret_cast<int*>(left_s + 4 * FWD_NWARPS * 128);
+    // TC5: two more tiles hold the TF32 hi / lo split of T_k (tcgen05 A operands); the leftover slots of the
+    // walk alias the head of the lo tile (written only after the MMAs of the step have completed)
+    unsigned char* Ahi = smem + (size_t)n_tbuf * tile_bytes;
+    unsigned char* Alo = Ahi + (TC5 ? tile_bytes : 0u);
+    unsigned char* Wimg = Alo + (TC5 ? tile_bytes : 0u);  // per layer: [hi rows][lo rows][8 bias rows]
+    unsigned char* left_s = TC5 ? Alo : Wimg + (size_t)p.w_rows_cap * 128;  // 4*NWARPS leftover slots of 128 B
+    int* csr0 = reinterpret_cast<int*>(Wimg + (size_t)p.w_rows_cap * 128 + (TC5 ? 0 : 4 * FWD_NWARPS * 128));
     const int rp_words = (p.rows_cap + 2 + 3) & ~3;
     const int csr_words = rp_words + p.nnz_cap * (HAS_VALS ? 2 : 1);
     const uint32_t smem_a = smem_u32(smem);
@@ -371,6 +391,18 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     // batch carries tile_info - with only ~2 tiles per CTA a static split leaves 30 % of the SMs idle in
     // the last round - else static round-robin.  The pipeline always knows the next TWO tile indices.
     int* s_idx = csr0 + (p.prefetch ? 2 : 1) * csr_words;  // two ints behind the CSR staging set(s)
+    // TC5: completion mbarrier (8 B) and the TMEM base address slot behind them
+    const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
+    const uint32_t ahi_a = smem_u32(Ahi), alo_a = smem_u32(Alo);
+    uint32_t tmem_base = 0, mma_phase = 0;
+    if (TC5) {
+        if (warp == 0) tmem_alloc(tslot, 32);
+        if (tid == 0) mbar_init(mbar, 1);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(s_idx + 4);
+    }
     const bool dyn = (p.sched != nullptr);
     int it = 0;
     int i_cur, i_nxt;
@@ -384,6 +416,11 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     }
     auto finish = [&]() {
         cp_async_wait<0>();
+        if (TC5) {
+            tc_fence_before();
+            __syncthreads();
+            if (warp == 0) tmem_dealloc(tmem_base, 32);
+        }
         if (dyn && tid == 0) {  // the last CTA out re-arms the counters for the next launch
             __threadfence();
             if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
@@ -417,6 +454,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
             cp_async_commit();
             cp_async_wait<0>();
         }
+        if (TC5) fence_proxy_async();  // cp.async-written weight images -> visible to the tensor-core proxy
         __syncthreads();
         // the tile after next: its index was published by the barrier, its bounds are consumed next iteration
         const int i_nn = dyn ? s_idx[it & 1] : (int)(blockIdx.x + (it + 2) * gridDim.x);
@@ -462,9 +500,9 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 
         for (int li = 0; li < p.n_layers; ++li) {
             const LayerDev& L = p.layers[li];
-            const int fi_pad = pad8(L.f_in), fo_pad = pad8(L.f_out);
+            const int fi_pad = pad8(L.f_in), fo_pad = pad8(L.f_out), fo_img = pad16(L.f_out);
             const int nchunks = fi_pad >> 3, nnt = fo_pad >> 3;
-            const int w_rows_l = L.K * fo_pad;
+            const int w_rows_l = L.K * fo_img;
             const int w_row0 = p.w_resident ? p.w_row_off[li] : 0;
             const uint32_t w_l = w_a + (uint32_t)w_row0 * 128u;
             const float* bias_s = reinterpret_cast<const float*>(Wimg + (size_t)(w_row0 + 2 * w_rows_l) * 128);
@@ -475,9 +513,15 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                 stage_weights_async(p, li, w_l, tid);
                 cp_async_commit();
                 cp_async_wait<0>();
+                if (TC5) fence_proxy_async();
                 __syncthreads();
             } else if (li > 0) {
                 __syncthreads();  // H_l written by the previous layer's epilogue
+            }
+            if (TC5) {  // A operands of T_0 (every MMA that read the split tiles has completed: the epilogue waited)
+                split_tile(bx, ahi_a, alo_a, n_mtiles, tid);
+                fence_proxy_async();
+                __syncthreads();
             }
 
             const int mslot = warp & (FWD_MSLOTS - 1), nt0 = (warp / FWD_MSLOTS) * 2;
@@ -492,17 +536,46 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 
             uint32_t tk = bx, tprev = bs;  // T_k, and the buffer T_{k+1} is written to (holds T_{k-1})
             for (int k = 0; k < L.K; ++k) {
-                const uint32_t whi_k = w_l + (uint32_t)(k * fo_pad) * 128u;
+                const uint32_t whi_k = w_l + (uint32_t)(k * fo_img) * 128u;
                 const uint32_t wlo_k = whi_k + (uint32_t)w_rows_l * 128u;
                 const bool more = (k + 1 < L.K) && !(p.debug & 1);
                 HeadState hs;
                 hs.pending = 0;
+                if (TC5) {
+                    // one thread feeds the tensor core: D[128 x fo_img] (+)= A_lo B_hi + A_hi B_lo + A_hi B_hi per 8-wide
+                    // K chunk, straight from the swizzled tiles; completion is signalled on the mbarrier
+                    if (tid == 0) {
+                        tc_fence_after();
+                        const uint32_t idesc = umma_idesc_tf32_m128((uint32_t)fo_img);
+                        for (int c = 0; c < nchunks; ++c) {
+                            const uint64_t a_hi = umma_desc_sw128(ahi_a + (uint32_t)c * 32u), a_lo = umma_desc_sw128(alo_a + (uint32_t)c * 32u);
+                            const uint64_t b_hi = umma_desc_sw128(whi_k + (uint32_t)c * 32u), b_lo = umma_desc_sw128(wlo_k + (uint32_t)c * 32u);
+                            umma_tf32(tmem_base, a_lo, b_hi, idesc, (k > 0 || c > 0) ? 1u : 0u);
+                            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+                            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+                        }
+                        umma_commit(mbar);
+                    }
+                    if (more) {
+                        // (the walk parks its leftovers in the head of the lo tile: wait for the MMAs first)
+                        if (k == 0) spmm_seg_walk<HAS_VALS, true, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
+                        else spmm_seg_walk<HAS_VALS, false, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
+                        __syncthreads();
+                        if (k == 0) spmm_fixup<true>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
+                        else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
+                        __syncthreads();
+                        mma_phase ^= 1u;  // every thread waited on this phase inside the walk
+                        split_tile(tprev, ahi_a, alo_a, n_mtiles, tid);
+                        fence_proxy_async();
+                    }
+                } else {
                 if (more) {
                     if (STAGED) {
-                        if (k == 0) spmm_seg_walk<HAS_VALS, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
-                        else spmm_seg_walk<HAS_VALS, false>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs);
+                        if (k == 0) spmm_seg_walk<HAS_VALS, true, false>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, 0u, 0u);
+                        else spmm_seg_walk<HAS_VALS, false, false>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, 0u, 0u);
+                    } else {
+                        spmm_rows_global<HAS_VALS>(tk, tprev, k == 0, rows, rp_s, p.b.colidx, p.b.vals, node0, warp, key);
                     }
-                    else spmm_rows_global<HAS_VALS>(tk, tprev, k == 0, rows, rp_s, p.b.colidx, p.b.vals, node0, warp, key);
                 }
                 // the dense contribution of T_k right behind the walk: warps that finish their segment early
                 // start on the tensor cores, so one barrier absorbs the imbalance of both
@@ -518,6 +591,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                     if (k == 0) spmm_fixup<true>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                     else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                 }
+                }
                 __syncthreads();
                 const uint32_t tmp = tk; tk = tprev; tprev = tmp;
             }
@@ -527,6 +601,39 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
             const int fo = L.f_out;
             float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
             const int g = lane >> 2, t4 = lane & 3;
+            if (TC5) {
+                // accumulator: TMEM lane = tile row, column = output feature.  warp w reads lane quadrant (w & 3),
+                // 8-column block (w >> 2): thread t holds row 32 q + t, columns 8 cb .. 8 cb + 7
+                mbar_wait(mbar, mma_phase);
+                mma_phase ^= 1u;
+                tc_fence_after();
+                const int q = warp & 3, cb = warp >> 2;
+                const int r = q * 32 + lane;
+                if (cb * 8 < fo_img) {
+                    uint32_t v[8];
+                    tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 8), v);
+                    float y[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = apply_act(__uint_as_float(v[j]) + bias_s[cb * 8 + j], L.act, L.slope);
+                    if (!last) {
+                        // columns >= f_out are exact zeros (zero W rows, zero bias, act(0) = 0)
+                        sts_f128(bx + swz_off((uint32_t)r, (uint32_t)(cb * 8)), make_float4(y[0], y[1], y[2], y[3]));
+                        sts_f128(bx + swz_off((uint32_t)r, (uint32_t)(cb * 8 + 4)), make_float4(y[4], y[5], y[6], y[7]));
+                    }
+                    if (gout != nullptr && r < rows) {
+                        float* dst = gout + (size_t)(node0 + r) * fo + cb * 8;
+                        if ((fo & 3) == 0 && cb * 8 + 8 <= fo) {
+                            *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (cb * 8 + j < fo) dst[j] = y[j];
+                        }
+                    }
+                }
+                tc_fence_before();  // TMEM reads ordered before the next layer's / tile's MMAs (which follow a barrier)
+            } else {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const int mt = mslot + m * FWD_MSLOTS;
@@ -560,6 +667,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                     }
                 }
             }
+            }  // !TC5
         }
         // rotate: the prefetched buffer becomes the next tile's X, the old X/scratch become scratch/prefetch
         if (!has_nxt) break;
@@ -578,16 +686,16 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 // -------------------------------------------------------------------------------------------
 // host launcher
 // -------------------------------------------------------------------------------------------
-static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, bool has_vals, bool prefetch) {
-    size_t s = (size_t)rows_cap * 128 * (prefetch ? 3 : 2) + (size_t)w_rows * 128 + 4 * FWD_NWARPS * 128;
+static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, bool has_vals, bool prefetch, bool tc5) {
+    size_t s = (size_t)rows_cap * 128 * ((prefetch ? 3 : 2) + (tc5 ? 2 : 0)) + (size_t)w_rows * 128 + (tc5 ? 0 : 4 * FWD_NWARPS * 128);
     const size_t csr_words = (size_t)((rows_cap + 2 + 3) & ~3) + (size_t)nnz_cap * (has_vals ? 2 : 1);
     s += csr_words * 4 * (prefetch ? 2 : 1);
-    return s + 16;  // + the scheduler's two index slots
+    return s + 32;  // + the scheduler's two index slots, the MMA completion mbarrier and the TMEM address slot
 }
 
-template <int MT, bool HAS_VALS, bool STAGED>
+template <int MT, bool HAS_VALS, bool STAGED, bool TC5 = false>
 static cudaError_t launch_one(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = cheb_forward_kernel<MT, HAS_VALS, STAGED>;
+    auto kern = cheb_forward_kernel<MT, HAS_VALS, STAGED, TC5>;
     // the attribute is sticky per (function, device): only raise it when a launch needs more
     static int smem_set[64] = {0};
     int dev = 0;
@@ -630,35 +738,43 @@ cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nn
     p.w_rows_cap = p.w_resident ? w_sum : w_max;
     if (!p.w_resident) for (int l = 0; l < p.n_layers; ++l) p.w_row_off[l] = 0;
 
-    // preference order: staged+prefetch with >=2 CTAs/SM, staged+prefetch, staged, global CSR
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+    // preference order: tcgen05 dense path (one 128-row M tile, no prefetch buffer), then
+    // staged+prefetch with >=2 CTAs/SM, staged+prefetch, staged, global CSR
     const int nnz_cap = (max_tile_nnz + 3) & ~3;
-    bool staged = true, prefetch = true;
-    size_t smem = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, true);
-    const size_t smem_np = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, false);
+    bool staged = true, prefetch = true, tc5 = false;
     auto per_sm_of = [&](size_t s) { int v = (int)((size_t)(228 * 1024) / (s + 1024)); return v > reg_limit ? reg_limit : v; };
-    if (smem > (size_t)max_smem_optin || (per_sm_of(smem) < 2 && per_sm_of(smem_np) >= 2 && reg_limit >= 2)) {
-        prefetch = false;
-        smem = smem_np;
+    size_t smem = 0;
+    if (mt_sel == 1 && !(dbg & 16)) {
+        p.rows_cap = 128;  // the UMMA M extent
+        const size_t s5 = fwd_smem_bytes(128, nnz_cap, p.w_rows_cap, has_vals, false, true);
+        if (s5 <= (size_t)max_smem_optin) { tc5 = true; prefetch = false; smem = s5; }
     }
-    if (smem > (size_t)max_smem_optin) {
-        staged = false;
-        smem = fwd_smem_bytes(p.rows_cap, 0, p.w_rows_cap, has_vals, false);
-        if (smem > (size_t)max_smem_optin) { *too_large = true; return cudaSuccess; }
+    if (!tc5) {
+        smem = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, true, false);
+        const size_t smem_np = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, false, false);
+        if (smem > (size_t)max_smem_optin || (per_sm_of(smem) < 2 && per_sm_of(smem_np) >= 2 && reg_limit >= 2) || (dbg & 8)) {
+            prefetch = false;
+            smem = smem_np;
+        }
+        if (smem > (size_t)max_smem_optin) {
+            staged = false;
+            smem = fwd_smem_bytes(p.rows_cap, 0, p.w_rows_cap, has_vals, false, false);
+            if (smem > (size_t)max_smem_optin) { *too_large = true; return cudaSuccess; }
+        }
     }
+    p.tc5 = tc5 ? 1 : 0;
     p.nnz_cap = staged ? nnz_cap : 0;
     p.prefetch = prefetch ? 1 : 0;
     if (p.b.tile_info == nullptr) p.sched = nullptr;  // static round-robin without a (sorted) tile_info
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
-        p.debug = dbg;
-        if (dbg & 8) { p.prefetch = 0; smem = smem_np; }
-    }
     int per_sm = per_sm_of(smem);
     if (per_sm < 1) per_sm = 1;
     int grid = num_sms * per_sm;
     if (grid > p.b.n_tiles) grid = p.b.n_tiles;
     if (grid < 1) grid = 1;
+    if (p.tc5) return has_vals ? launch_one<1, true, true, true>(p, grid, smem, st) : launch_one<1, false, true, true>(p, grid, smem, st);
     switch (mt_sel) {
         case 1: return launch_mt<1>(p, has_vals, staged, grid, smem, st);
         case 2: return launch_mt<2>(p, has_vals, staged, grid, smem, st);

@@ -156,6 +156,62 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope
     return 1.f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 (5th-generation tensor core) helpers: TMEM allocation, UMMA descriptors, MMA issue,
+// completion barrier, TMEM -> register loads.  cta_group::1 only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem_addr, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "MHO_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra MHO_DONE_%=;\n\t"
+        "bra MHO_WAIT_%=;\n\t"
+        "MHO_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups, version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {  // arrive on `bar` once every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __host__ __device__ __forceinline__ int pad8(int x) { return (x + 7) & ~7; }
 __host__ __device__ __forceinline__ int pad16(int x) { return (x + 15) & ~15; }
 
@@ -198,5 +254,6 @@ struct FwdParams {
     int* sched;       // {next tile counter, finished-CTA counter} in device memory (dynamic scheduler) or NULL
     int prefetch;     // 1: third tile buffer + second CSR staging set, next tile fetched with cp.async
     int total_nodes;
+    int tc5;          // 1: dense part on tcgen05.mma (TMEM accumulators); needs rows_cap <= 128
     int debug;        // MHO_DEBUG env (perf experiments only): 1 skip sparse step, 2 skip mma, 8 no prefetch
 };
