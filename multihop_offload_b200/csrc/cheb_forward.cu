@@ -339,15 +339,20 @@ __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileI
     }
 }
 
-// split one [rows_cap][32] fp32 tile into TF32 hi / lo tiles (same swizzled layout): the tcgen05 A operands
-__device__ __forceinline__ void split_tile(uint32_t src, uint32_t ahi, uint32_t alo, int n_rows16, int tid) {
+// tcgen05 A operands of a [rows_cap][32] fp32 tile: the tile itself serves as the "hi" part - kind::tf32 reads
+// fp32 words and ignores the low 13 mantissa bits (verified on B200: tests pass with errors ~1e-6) - and this
+// pass writes the matching "lo" tile, lo = rn_tf32(x - trunc_tf32(x)), in the same swizzled layout.
+__device__ __forceinline__ void split_tile_lo(uint32_t src, uint32_t alo, int n_rows16, int tid) {
     for (int idx = tid; idx < n_rows16 * 16 * 8; idx += FWD_THREADS) {
         const uint32_t off = (uint32_t)idx << 4;  // (row, physical chunk) -> byte offset; the swizzle is a permutation
         const float4 v = lds_f128(src + off);
-        uint32_t h[4], l[4];
-        split_tf32_fast(v.x, h[0], l[0]); split_tf32_fast(v.y, h[1], l[1]);
-        split_tf32_fast(v.z, h[2], l[2]); split_tf32_fast(v.w, h[3], l[3]);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ahi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]));
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        uint32_t l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float hi = __uint_as_float(__float_as_uint(x[i]) & 0xffffe000u);
+            l[i] = (__float_as_uint(x[i] - hi) + 0x1000u) & 0xffffe000u;
+        }
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(alo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]));
     }
 }
@@ -363,10 +368,9 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     // ---- shared memory carve-up
     const uint32_t tile_bytes = (uint32_t)p.rows_cap * 128u;
     const int n_tbuf = p.prefetch ? 3 : 2;
-    // TC5: two more tiles hold the TF32 hi / lo split of T_k (tcgen05 A operands); the leftover slots of the
-    // walk alias the head of the lo tile (written only after the MMAs of the step have completed)
-    unsigned char* Ahi = smem + (size_t)n_tbuf * tile_bytes;
-    unsigned char* Alo = Ahi + (TC5 ? tile_bytes : 0u);
+    // TC5: one more tile holds the TF32 "lo" part of T_k (the fp32 tile itself is the "hi" tcgen05 operand); the
+    // leftover slots of the walk alias the head of the lo tile (written only after the step's MMAs completed)
+    unsigned char* Alo = smem + (size_t)n_tbuf * tile_bytes;
     unsigned char* Wimg = Alo + (TC5 ? tile_bytes : 0u);  // per layer: [hi rows][lo rows][8 bias rows]
     unsigned char* left_s = TC5 ? Alo : Wimg + (size_t)p.w_rows_cap * 128;  // 4*NWARPS leftover slots of 128 B
     int* csr0 = reinterpret_cast<int*>(Wimg + (size_t)p.w_rows_cap * 128 + (TC5 ? 0 : 4 * FWD_NWARPS * 128));
@@ -376,7 +380,11 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     const uint32_t w_a = smem_u32(Wimg);
     const uint32_t csr_a0 = smem_u32(csr0);
     const uint32_t left_base = smem_u32(left_s);
-    const int group = warp * 4 + (lane >> 3);
+    // TC5: warp 0 feeds the tensor core (MMA issue costs its elected thread a few hundred cycles per step), so it
+    // sits out the walk: 4*(NWARPS-1) lane groups over warps 1..; otherwise every warp walks
+    constexpr int NGROUPS = TC5 ? 4 * (FWD_NWARPS - 1) : 4 * FWD_NWARPS;
+    const bool walker = !TC5 || warp > 0;
+    const int group = walker ? (warp - (TC5 ? 1 : 0)) * 4 + (lane >> 3) : NGROUPS;  // NGROUPS = "no segment"
     const uint32_t left_a = left_base + (uint32_t)group * 128u + ckey;
 
     // rotating tile buffers: bx = T_0 / X of the current tile, bs = scratch, bp = prefetch target
@@ -393,7 +401,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     int* s_idx = csr0 + (p.prefetch ? 2 : 1) * csr_words;  // two ints behind the CSR staging set(s)
     // TC5: completion mbarrier (8 B) and the TMEM base address slot behind them
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
-    const uint32_t ahi_a = smem_u32(Ahi), alo_a = smem_u32(Alo);
+    const uint32_t alo_a = smem_u32(Alo);
     uint32_t tmem_base = 0, mma_phase = 0;
     if (TC5) {
         if (warp == 0) tmem_alloc(tslot, 32);
@@ -472,7 +480,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                 sts_u32(pre_a + e * 4, swz_row(lds_u32(pre_a + e * 4) - (uint32_t)node0));
             // ... the group's segment of the entry stream and the row it starts in ...
             {
-                const int L = (cur.nnz + 4 * FWD_NWARPS - 1) / (4 * FWD_NWARPS);
+                const int L = (cur.nnz + NGROUPS - 1) / NGROUPS;
                 sg.seg_len = L > 0 ? L : 1;
                 const int sb = min(group * sg.seg_len, cur.nnz);
                 sg.sb = sb;
@@ -519,13 +527,14 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                 __syncthreads();  // H_l written by the previous layer's epilogue
             }
             if (TC5) {  // A operands of T_0 (every MMA that read the split tiles has completed: the epilogue waited)
-                split_tile(bx, ahi_a, alo_a, n_mtiles, tid);
-                fence_proxy_async();
+                split_tile_lo(bx, alo_a, n_mtiles, tid);
+                fence_proxy_async();  // also publishes the generic-proxy writes of bx (epilogue / cp.async) to the tensor core
                 __syncthreads();
             }
 
             const int mslot = warp & (FWD_MSLOTS - 1), nt0 = (warp / FWD_MSLOTS) * 2;
             const bool has_n = nt0 < nnt;  // this warp's n-tile half exists for this layer
+            const uint32_t idesc = umma_idesc_tf32_m128((uint32_t)fo_img);
             float acc[MT][2][4];
 #pragma unroll
             for (int m = 0; m < MT; ++m)
@@ -546,27 +555,36 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                     // K chunk, straight from the swizzled tiles; completion is signalled on the mbarrier
                     if (tid == 0) {
                         tc_fence_after();
-                        const uint32_t idesc = umma_idesc_tf32_m128((uint32_t)fo_img);
+                        // D[128 x fo_img] (+)= A_lo B_lo + A_lo B_hi + A_hi B_lo + A_hi B_hi per 8-wide K chunk; descriptors
+                        // advance by 32 B (= +2 in the >>4 address field) per chunk
+                        uint64_t a_hi = umma_desc_sw128(tk), a_lo = umma_desc_sw128(alo_a);
+                        uint64_t b_hi = umma_desc_sw128(whi_k), b_lo = umma_desc_sw128(wlo_k);
+                        uint32_t accum = k > 0 ? 1u : 0u;
                         for (int c = 0; c < nchunks; ++c) {
-                            const uint64_t a_hi = umma_desc_sw128(ahi_a + (uint32_t)c * 32u), a_lo = umma_desc_sw128(alo_a + (uint32_t)c * 32u);
-                            const uint64_t b_hi = umma_desc_sw128(whi_k + (uint32_t)c * 32u), b_lo = umma_desc_sw128(wlo_k + (uint32_t)c * 32u);
-                            umma_tf32(tmem_base, a_lo, b_hi, idesc, (k > 0 || c > 0) ? 1u : 0u);
+                            umma_tf32(tmem_base, a_lo, b_lo, idesc, accum);
+                            umma_tf32(tmem_base, a_lo, b_hi, idesc, 1u);
                             umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
                             umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+                            accum = 1u;
+                            a_hi += 2; a_lo += 2; b_hi += 2; b_lo += 2;
                         }
                         umma_commit(mbar);
                     }
                     if (more) {
                         // (the walk parks its leftovers in the head of the lo tile: wait for the MMAs first)
-                        if (k == 0) spmm_seg_walk<HAS_VALS, true, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
-                        else spmm_seg_walk<HAS_VALS, false, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
+                        if (walker) {
+                            if (k == 0) spmm_seg_walk<HAS_VALS, true, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
+                            else spmm_seg_walk<HAS_VALS, false, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
+                        } else {
+                            mbar_wait(mbar, mma_phase);  // keep the phase bookkeeping identical on every thread
+                        }
                         __syncthreads();
                         if (k == 0) spmm_fixup<true>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                         else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                         __syncthreads();
                         mma_phase ^= 1u;  // every thread waited on this phase inside the walk
-                        split_tile(tprev, ahi_a, alo_a, n_mtiles, tid);
-                        fence_proxy_async();
+                        split_tile_lo(tprev, alo_a, n_mtiles, tid);
+                        fence_proxy_async();  // lo tile AND the walk's generic-proxy writes of T_{k+1} -> tensor-core proxy
                     }
                 } else {
                 if (more) {
@@ -687,7 +705,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
 // host launcher
 // -------------------------------------------------------------------------------------------
 static size_t fwd_smem_bytes(int rows_cap, int nnz_cap, int w_rows, bool has_vals, bool prefetch, bool tc5) {
-    size_t s = (size_t)rows_cap * 128 * ((prefetch ? 3 : 2) + (tc5 ? 2 : 0)) + (size_t)w_rows * 128 + (tc5 ? 0 : 4 * FWD_NWARPS * 128);
+    size_t s = (size_t)rows_cap * 128 * ((prefetch ? 3 : 2) + (tc5 ? 1 : 0)) + (size_t)w_rows * 128 + (tc5 ? 0 : 4 * FWD_NWARPS * 128);
     const size_t csr_words = (size_t)((rows_cap + 2 + 3) & ~3) + (size_t)nnz_cap * (has_vals ? 2 : 1);
     s += csr_words * 4 * (prefetch ? 2 : 1);
     return s + 32;  // + the scheduler's two index slots, the MMA completion mbarrier and the TMEM address slot
@@ -749,8 +767,10 @@ cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nn
     size_t smem = 0;
     if (mt_sel == 1 && !(dbg & 16)) {
         p.rows_cap = 128;  // the UMMA M extent
+        const size_t s5p = fwd_smem_bytes(128, nnz_cap, p.w_rows_cap, has_vals, true, true);
         const size_t s5 = fwd_smem_bytes(128, nnz_cap, p.w_rows_cap, has_vals, false, true);
-        if (s5 <= (size_t)max_smem_optin) { tc5 = true; prefetch = false; smem = s5; }
+        if (s5p <= (size_t)max_smem_optin && per_sm_of(s5p) >= 2 && !(dbg & 8)) { tc5 = true; prefetch = true; smem = s5p; }
+        else if (s5 <= (size_t)max_smem_optin) { tc5 = true; prefetch = false; smem = s5; }
     }
     if (!tc5) {
         smem = fwd_smem_bytes(p.rows_cap, nnz_cap, p.w_rows_cap, has_vals, true, false);
