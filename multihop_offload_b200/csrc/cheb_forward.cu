@@ -186,12 +186,14 @@ __device__ __forceinline__ void emit_row(uint32_t Tdst, int row, uint32_t ckey, 
     }
 }
 
+// (returns the next non-empty row by value: a by-reference row would live in local memory)
 template <bool FIRST>
-__device__ __noinline__ void emit_empty_rows(uint32_t Tdst, int& row, int rows, const int* rp_s, uint32_t ckey) {
+__device__ __noinline__ int emit_empty_rows(uint32_t Tdst, int row, int rows, const int* rp_s, uint32_t ckey) {
     while (row < rows && rp_s[row + 1] == rp_s[row]) {
         emit_row<FIRST>(Tdst, row, ckey, make_float4(0.f, 0.f, 0.f, 0.f));
         ++row;
     }
+    return row;
 }
 
 // one stream entry: gather, accumulate
@@ -214,8 +216,7 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, cons
     hs.head_row = 0;
     hs.head = make_float4(0.f, 0.f, 0.f, 0.f);
     if (is_group0) {  // empty rows in front of the first stored entry belong to nobody's stream
-        int r = 0;
-        emit_empty_rows<FIRST>(Tdst, r, rows, rp_s, ckey);
+        emit_empty_rows<FIRST>(Tdst, 0, rows, rp_s, ckey);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sg.n > 0) {
@@ -237,7 +238,7 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, cons
                     hs.head = acc; hs.head_row = row; hs.pending = 1;
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
                     ++row;
-                    if (cur & 2u) emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
+                    if (cur & 2u) row = emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
                     break;
                 }
                 if (ea >= ea_end) break;
@@ -256,7 +257,7 @@ __device__ __forceinline__ void spmm_seg_walk(uint32_t Tsrc, uint32_t Tdst, cons
                 emit_row<FIRST>(Tdst, row, ckey, acc);
                 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 ++row;
-                if (cur & 2u) emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
+                if (cur & 2u) row = emit_empty_rows<FIRST>(Tdst, row, rows, rp_s, ckey);
             }
         }
     }
