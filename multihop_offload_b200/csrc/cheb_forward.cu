@@ -20,6 +20,7 @@
 //     ldmatrix, interleaved with the sparse step for T_{k+1};
 //   * HBM traffic per tile is exactly X in, Y out, CSR once; T_k never leaves the SM.
 #include <cstdlib>
+#include <cstring>
 
 #include "mho_common.cuh"
 
@@ -363,6 +364,9 @@ __global__ void __launch_bounds__(FWD_THREADS, (MT == 1 ? 2 : 1))
 cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // programmatic dependent launch: let the next launch in the stream start filling SM slots as soon as this
+    // grid's CTAs drain; it parks at griddepcontrol.wait (below) until this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t key = swz_key((uint32_t)lane);        // lane = feature layout (global-CSR fallback)
     const uint32_t ckey = ((uint32_t)lane & 7u) << 4;    // lane = 16 B chunk layout (stream walk)
 
@@ -392,6 +396,9 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
     uint32_t bx = smem_a, bs = smem_a + tile_bytes, bp = smem_a + 2u * tile_bytes;
     int cs = 0;  // CSR staging set of the current tile
 
+    // everything above touched only this CTA's shared / tensor memory; from here on global memory written by
+    // earlier launches in the stream is read (weights image, scheduler counters, inputs)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // resident weights ride in the first cp.async group (waited for before the first tile computes)
     if (p.w_resident)
         for (int l = 0; l < p.n_layers; ++l) stage_weights_async(p, l, w_a + (uint32_t)p.w_row_off[l] * 128u, tid);
@@ -724,8 +731,18 @@ static cudaError_t launch_one(const FwdParams& p, int grid, size_t smem, cudaStr
         if (e != cudaSuccess) return e;
         smem_set[dev & 63] = (int)smem;
     }
-    kern<<<grid, FWD_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FWD_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <int MT>
