@@ -583,14 +583,15 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                         if (walker) {
                             if (k == 0) spmm_seg_walk<HAS_VALS, true, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
                             else spmm_seg_walk<HAS_VALS, false, true>(tk, tprev, sg, rows, rp_s, pre_a, val_a, ckey, left_a, group == 0, hs, mbar, mma_phase);
-                        } else {
-                            mbar_wait(mbar, mma_phase);  // keep the phase bookkeeping identical on every thread
                         }
                         __syncthreads();
                         if (k == 0) spmm_fixup<true>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                         else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                         __syncthreads();
-                        mma_phase ^= 1u;  // every thread waited on this phase inside the walk
+                        // (walkers waited on this phase inside the walk; the MMA warp checks once here - long complete -
+                        //  instead of spinning on the barrier while the others walk)
+                        if (!walker) mbar_wait(mbar, mma_phase);
+                        mma_phase ^= 1u;
                         split_tile_lo(tprev, alo_a, n_mtiles, tid);
                         fence_proxy_async();  // lo tile AND the walk's generic-proxy writes of T_{k+1} -> tensor-core proxy
                     }
