@@ -175,3 +175,45 @@ def test_full_size_linearity_property(torch_cuda):
         a, b = off[gi], off[gi + 1]
         ref = O.cheb_stack_forward(mats[gi], Xh[a:b], ws, [O.ACT_NONE])
         assert rel_err(Y1[a:b].cpu().numpy(), ref) < TOL
+
+
+def test_host_api_multichunk_pipeline_equals_device_api(torch_cuda):
+    """1024 graphs -> ~600 tiles -> the host call runs as 3 pipelined chunks (upload / kernel / download
+    streams); the result must equal the single-launch device path bit for bit (same tiles, same order of
+    floating-point operations inside every tile), with and without operator values."""
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    rng = np.random.default_rng(3)
+    sizes = rng.choice(np.arange(20, 111, 10), size=1024)
+    mats = O.make_batch(sizes, seed0=5000)
+    for weighted in (False, True):
+        if weighted:
+            mats = [sp.csr_matrix((rng.uniform(-0.3, 0.3, size=m.nnz), m.indices, m.indptr), shape=m.shape) for m in mats]
+        specs = [LayerSpec(3, 32, 32)]
+        ws = random_weights(specs, rng, 0.5)
+        net = _net(specs, ws)
+        batch = GraphBatch.from_scipy(mats, binary=not weighted, device="cuda:0")
+        X = rng.normal(size=(batch.total_nodes, 32)).astype(np.float32)
+        Yd = net.forward(batch, torch_cuda.from_numpy(X).cuda()).cpu().numpy()
+        Yh = net.forward_host(batch.graph_off, batch.rowptr, batch.colidx, batch.vals, X)
+        assert np.array_equal(Yd, Yh)
+        off = batch.graph_off
+        for gi in rng.choice(len(mats), size=8, replace=False):
+            ref = O.cheb_stack_forward(mats[gi], X[off[gi]:off[gi + 1]].astype(np.float64), ws, [specs[0].act])
+            assert rel_err(Yh[off[gi]:off[gi + 1]], ref) < TOL
+
+
+def test_weights_change_is_picked_up(torch_cuda):
+    """The packed TF32 weight images are cached per context: set_weights / the optimizer must invalidate them."""
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    rng = np.random.default_rng(4)
+    mats = O.make_batch([40, 50], seed0=1)
+    specs = [LayerSpec(2, 32, 32)]
+    net = _net(specs, random_weights(specs, rng, 0.5))
+    batch = GraphBatch.from_scipy(mats, device="cuda:0")
+    X = rng.normal(size=(90, 32))
+    Xd = torch_cuda.from_numpy(X.astype(np.float32)).cuda()
+    for _ in range(3):
+        ws = random_weights(specs, rng, 0.5)
+        net.set_weights(ws)
+        Y = net.forward(batch, Xd).cpu().numpy()
+        assert rel_err(Y, oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2), batch.graph_off) < TOL
