@@ -619,7 +619,16 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                     else spmm_fixup<false>(tprev, sg, group, rp_s, nz0, ckey, left_base, hs);
                 }
                 }
-                __syncthreads();
+                if (TC5) {
+                    // only the MMA warp needs everybody's lo-tile slice before it feeds the tensor core again; the
+                    // walkers just signal and move on (their next gathers need T_{k+1}, final since the last barrier)
+                    if (more) {
+                        if (warp == 0) asm volatile("bar.sync 1, %0;" ::"n"(FWD_THREADS) : "memory");
+                        else asm volatile("bar.arrive 1, %0;" ::"n"(FWD_THREADS) : "memory");
+                    }
+                } else {
+                    __syncthreads();
+                }
                 const uint32_t tmp = tk; tk = tprev; tprev = tmp;
             }
 
