@@ -57,6 +57,8 @@ PROTOTYPES = [
     ("mho_adam_replay", C.c_int, [C.c_void_p, C.POINTER(mho_layer_t), C.c_int32, C.POINTER(mho_adam_t),
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_int64, C.c_void_p]),
+    ("mho_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    ("mho_host_free", C.c_int, [C.c_void_p]),
     ("mho_cheb_forward_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(mho_layer_t), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]
@@ -117,3 +119,35 @@ class Context:
                 self.handle = C.c_void_p()
         except Exception:
             pass
+
+
+class PinnedArray:
+    """numpy array over a cudaHostAlloc'd buffer (mho_host_alloc); freed with the object."""
+
+    def __init__(self, shape, dtype):
+        import numpy as np
+        self.lib = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self.ptr = C.c_void_p()
+        check(self.lib.mho_host_alloc(C.byref(self.ptr), n), "mho_host_alloc")
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self.lib.mho_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_like(a):
+    """Copy a numpy array into page-locked memory; returns the PinnedArray (use .array)."""
+    import numpy as np
+    a = np.ascontiguousarray(a)
+    p = PinnedArray(a.shape, a.dtype)
+    p.array[...] = a
+    return p

@@ -72,6 +72,18 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     return MHO_OK;
 }
 
+extern "C" int mho_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) { mho_set_error("mho_host_alloc: ptr is NULL"); return MHO_ERR_INVALID; }
+    *ptr = nullptr;
+    CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MHO_OK;
+}
+
+extern "C" int mho_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return MHO_OK;
+}
+
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
 
 extern "C" int mho_invalidate_weights(mho_ctx_t* c) {

@@ -15,3 +15,18 @@ def d2h():
 def both(): h2d(); d2h()
 a=t(h2d); b=t(d2h); c=t(both)
 print("H2D %.1f MB: %.3f ms (%.1f GB/s)  D2H %.1f MB: %.3f ms (%.1f GB/s)  both: %.3f ms" % (x.numel()*4/1e6, a, x.numel()*4/a/1e6, y.numel()*4/1e6, b, y.numel()*4/b/1e6, c))
+
+# write-combined pinned memory (cudaHostAllocWriteCombined = 4) vs torch's default pinned memory
+import ctypes as C
+rt = C.CDLL("libcudart.so.12")
+n = x.numel() * 4
+for flags, name in ((0, "default"), (4, "write-combined"), (1, "portable")):
+    p = C.c_void_p()
+    assert rt.cudaHostAlloc(C.byref(p), C.c_size_t(n), C.c_uint(flags)) == 0
+    C.memset(p, 1, n)
+    st = torch.cuda.current_stream().cuda_stream
+    def f():
+        rt.cudaMemcpyAsync(C.c_void_p(dx.data_ptr()), p, C.c_size_t(n), C.c_int(1), C.c_void_p(st))
+    ms = t(f)
+    print("cudaHostAlloc(%s): H2D %.3f ms (%.1f GB/s)" % (name, ms, n / ms / 1e6))
+    rt.cudaFreeHost(p)
