@@ -144,6 +144,30 @@ int mho_adam_replay(mho_ctx_t* ctx, const mho_layer_t* layers, int32_t n_layers,
                     const mho_adam_t* cfg, double* params, double* m, double* v, float* params_f32,
                     const float* grads, int32_t n_steps, int64_t step_count, mho_stream_t stream);
 
+/* ---- queue-model head that follows the GNN: replaces the TensorFlow op chain of ACOAgent.forward,
+ * gnn_offloading_agent.py:231-254 (gathers, 10 fixed-point iterations mu <- r / (1 + A_i clip(lambda/mu, 0, 1)),
+ * M/M/1 delays with the congestion branch) and its VJP (the head part of :448, through all ten iterations),
+ * fused and batched, fp64 like the reference.  All arrays are device pointers; graphs are concatenated:
+ * ext_off (= the GNN batch's graph_off), link_off, comp_off [n_graphs+1]; maps_* hold LOCAL extended-edge ids
+ * (obj.maps_ol_el / obj.maps_on_el); adj_rowptr [total_links+1] global offsets, adj_colidx LOCAL link ids of the
+ * symmetric conflict graph env.adj_i; node_mu = proc_bws[proc_bws > 0]. */
+typedef struct {
+    int32_t n_graphs, max_links;           /* max_links: largest per-graph link count (shared-memory sizing) */
+    int64_t total_links, total_comp, total_adj_nnz;
+    const int32_t* ext_off; const int32_t* link_off; const int32_t* comp_off;
+    const int32_t* maps_ol_el; const int32_t* maps_on_el;
+    const double* link_rates; const double* cf_degs; const double* node_mu;
+    const int32_t* adj_rowptr; const int32_t* adj_colidx;
+    double T;                              /* env.T, the congestion-penalty constant */
+} mho_head_t;
+/* lam [total_ext] fp32 (the GNN output) -> link_delay [total_links], node_delay [total_comp] (fp64);
+ * saved_mu (nullable) [11 * total_links] keeps mu_0..mu_10 for the backward */
+int mho_queue_head_forward(mho_ctx_t* ctx, const mho_head_t* head, const float* lam, double* link_delay,
+                           double* node_delay, double* saved_mu, mho_stream_t stream);
+/* g_link / g_node: gradients wrt the delays -> g_lam [total_ext] fp32 (the dY of mho_cheb_backward) */
+int mho_queue_head_backward(mho_ctx_t* ctx, const mho_head_t* head, const float* lam, const double* saved_mu,
+                            const double* g_link, const double* g_node, float* g_lam, mho_stream_t stream);
+
 /* ---- host-buffer convenience (the reference-facing call: numpy in, numpy out, as
  * ACOAgent.predict takes them).  All pointers are HOST memory (pinned for full speed); the
  * call uploads the batch + X, runs mho_cheb_forward, downloads Y and synchronises `stream`.

@@ -30,6 +30,13 @@ class mho_layer_t(C.Structure):
                 ("slope", C.c_float), ("W", C.c_void_p), ("b", C.c_void_p)]
 
 
+class mho_head_t(C.Structure):
+    _fields_ = [("n_graphs", C.c_int32), ("max_links", C.c_int32), ("total_links", C.c_int64), ("total_comp", C.c_int64),
+                ("total_adj_nnz", C.c_int64), ("ext_off", C.c_void_p), ("link_off", C.c_void_p), ("comp_off", C.c_void_p),
+                ("maps_ol_el", C.c_void_p), ("maps_on_el", C.c_void_p), ("link_rates", C.c_void_p), ("cf_degs", C.c_void_p),
+                ("node_mu", C.c_void_p), ("adj_rowptr", C.c_void_p), ("adj_colidx", C.c_void_p), ("T", C.c_double)]
+
+
 class mho_adam_t(C.Structure):
     _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
                 ("clipnorm", C.c_double), ("max_norm", C.c_double), ("decay_rate", C.c_double),
@@ -57,6 +64,10 @@ PROTOTYPES = [
     ("mho_adam_replay", C.c_int, [C.c_void_p, C.POINTER(mho_layer_t), C.c_int32, C.POINTER(mho_adam_t),
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_int64, C.c_void_p]),
+    ("mho_queue_head_forward", C.c_int, [C.c_void_p, C.POINTER(mho_head_t), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    ("mho_queue_head_backward", C.c_int, [C.c_void_p, C.POINTER(mho_head_t), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     ("mho_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     ("mho_host_free", C.c_int, [C.c_void_p]),
     ("mho_cheb_forward_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

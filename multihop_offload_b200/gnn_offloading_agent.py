@@ -153,6 +153,7 @@ class ACOAgent:
         self.reward_mem = deque(maxlen=memory_size)
         self._tape = None
         self._adj_cache = {}
+        self._head_cache = {}
 
     def _build_model(self):
         """:81-123 - num_layer ChebConv layers, 4 -> 32 -> ... -> 1, leaky_relu x (L-1) + relu, Adam(clipnorm=1)."""
@@ -258,17 +259,33 @@ class ACOAgent:
         state = self.makestate(adj, node_features)
         lambda_array = self.act(state, save=save)
 
-        hi = qh.HeadInputs(obj, env, self.device)
-        lam64 = lambda_array.detach().to(torch.float64)
-        if save:
-            lam64.requires_grad_(True)
-        link_lambda = lam64[hi.maps_ol_el]
-        node_lambda = lam64[hi.maps_on_el]
-        link_delay, node_delay = qh.queue_delays(link_lambda, node_lambda, hi.link_rates, hi.cf_degs, hi.node_mu,
-                                                 hi.adj_i, hi.T)
+        fused = str(self.device).startswith("cuda") and hasattr(self.net, "ctx")
+        if fused:
+            # fused fp64 head kernels (csrc/queue_head.cu); the per-network constants are cached on the device
+            hi = qh.HeadInputs(obj, env, None)
+            key = (id(env), hi.link_rates_host.tobytes(), hi.node_mu_host.tobytes(), hi.maps_ol_el_host.tobytes())
+            hb = self._head_cache.get(key)
+            if hb is None:
+                if len(self._head_cache) > 32:
+                    self._head_cache.clear()
+                hb = qh.HeadBatch([hi], [nn], self.net.ctx, self.device)
+                self._head_cache[key] = hb
+            ld, nd = hb.forward(lambda_array, save=save)
+            link_delay, node_delay = ld.reshape(-1, 1), nd.reshape(-1, 1)
+            lam64 = None
+        else:
+            hi = qh.HeadInputs(obj, env, self.device)
+            hb = None
+            lam64 = lambda_array.detach().to(torch.float64)
+            if save:
+                lam64.requires_grad_(True)
+            link_lambda = lam64[hi.maps_ol_el]
+            node_lambda = lam64[hi.maps_on_el]
+            link_delay, node_delay = qh.queue_delays(link_lambda, node_lambda, hi.link_rates, hi.cf_degs, hi.node_mu,
+                                                     hi.adj_i, hi.T)
         delay_mtx_ts, delay_mtx_np = qh.delay_matrices(link_delay, node_delay, hi, self.bug_compatible)
         if save:
-            self._tape.update(lam64=lam64, link_delay=link_delay, node_delay=node_delay, hi=hi)
+            self._tape.update(lam64=lam64, link_delay=link_delay, node_delay=node_delay, hi=hi, hb=hb)
         return state, delay_mtx_ts, delay_mtx_np
 
     def forward_env(self, obj, env):
@@ -380,11 +397,14 @@ class ACOAgent:
         -> libmho's ChebConv VJP.  Returns the flat gradient (kernel_0, bias_0, ...) as a device tensor."""
         import torch
         tape = self._tape
-        if tape is None or "lam64" not in tape:
+        if tape is None or "hi" not in tape:
             raise RuntimeError("no taped forward: call forward(obj, env, save=True) first")
         g_ld, g_nd = qh.seed_from_grad_dist(grad_dist_np, tape["hi"], self.device)
-        (g_lam,) = torch.autograd.grad([tape["link_delay"], tape["node_delay"]], tape["lam64"], [g_ld, g_nd])
-        dY = g_lam.to(torch.float32).contiguous()
+        if tape["hb"] is not None:
+            dY = tape["hb"].backward(g_ld, g_nd).contiguous()
+        else:
+            (g_lam,) = torch.autograd.grad([tape["link_delay"], tape["node_delay"]], tape["lam64"], [g_ld, g_nd])
+            dY = g_lam.to(torch.float32).contiguous()
         gpg, _, _ = self.net.backward(tape["batch"], tape["X"], tape["Y"], tape["saved"], dY, need_sum=False)
         return gpg[0]
 

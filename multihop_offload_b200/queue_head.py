@@ -67,17 +67,24 @@ class HeadInputs:
     """Per-(network, instance) constants of the head, on `device` in float64 (env fields of :233-238)."""
 
     def __init__(self, obj, env, device):
-        f64 = dict(dtype=torch.float64, device=device)
-        self.maps_ol_el = torch.as_tensor(np.asarray(obj.maps_ol_el, dtype=np.int64), device=device)
-        self.maps_on_el = torch.as_tensor(np.asarray(obj.maps_on_el, dtype=np.int64), device=device)
+        f64 = dict(dtype=torch.float64, device=device if device is not None else "cpu")
+        self.maps_ol_el_host = np.asarray(obj.maps_ol_el, dtype=np.int64)
+        self.maps_on_el_host = np.asarray(obj.maps_on_el, dtype=np.int64)
         proc = np.asarray(env.proc_bws, dtype=np.float64).reshape(-1)
         self.comp_nodes = np.nonzero(proc > 0)[0]
-        self.node_mu = torch.as_tensor(proc[self.comp_nodes].reshape(-1, 1), **f64)
-        self.link_rates = torch.as_tensor(np.asarray(env.link_rates, dtype=np.float64), **f64)
-        self.cf_degs = torch.as_tensor(np.asarray(env.cf_degs, dtype=np.float64), **f64)
-        adj = env.adj_i
-        adj = adj.toarray() if hasattr(adj, "toarray") else np.asarray(adj)
-        self.adj_i = torch.as_tensor(adj.astype(np.float64), **f64)
+        self.node_mu_host = proc[self.comp_nodes]
+        self.link_rates_host = np.asarray(env.link_rates, dtype=np.float64).reshape(-1)
+        self.cf_degs_host = np.asarray(env.cf_degs, dtype=np.float64).reshape(-1)
+        self.adj_i_host = env.adj_i
+        if device is not None:  # torch copies for the autograd implementation (critic on the CPU, tests)
+            self.maps_ol_el = torch.as_tensor(self.maps_ol_el_host, device=device)
+            self.maps_on_el = torch.as_tensor(self.maps_on_el_host, device=device)
+            self.node_mu = torch.as_tensor(self.node_mu_host.reshape(-1, 1), **f64)
+            self.link_rates = torch.as_tensor(self.link_rates_host, **f64)
+            self.cf_degs = torch.as_tensor(self.cf_degs_host, **f64)
+            adj = env.adj_i
+            adj = adj.toarray() if hasattr(adj, "toarray") else np.asarray(adj)
+            self.adj_i = torch.as_tensor(adj.astype(np.float64), **f64)
         self.T = float(env.T)
         self.num_nodes = int(env.num_nodes)
         self.num_links = int(env.num_links)
@@ -148,3 +155,70 @@ def critic(routes_np, jobs_load, jobs_data, obj, hi_cpu: HeadInputs, num_edges_e
     loss = delay_job_edge.sum()
     (grad_routes,) = torch.autograd.grad(loss, routes)
     return float(loss.item()), grad_routes.numpy(), delay_job_edge.detach().numpy(), unit.detach().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# fused, batched head on the device (csrc/queue_head.cu through the C-ABI)
+# ---------------------------------------------------------------------------------------------
+class HeadBatch:
+    """Device-resident head constants of B (network, instance) graphs, concatenated (mho_head_t)."""
+
+    def __init__(self, his, ext_sizes, ctx, device):
+        import ctypes as C
+        from . import _lib
+        self.ctx, self.device, self.his = ctx, torch.device(device), list(his)
+        B = len(self.his)
+        ext_off = np.concatenate([[0], np.cumsum(ext_sizes)]).astype(np.int32)
+        link_off = np.concatenate([[0], np.cumsum([h.num_links for h in self.his])]).astype(np.int32)
+        comp_off = np.concatenate([[0], np.cumsum([len(h.comp_nodes) for h in self.his])]).astype(np.int32)
+        rp, ci, z = [np.zeros(1, dtype=np.int64)], [], 0
+        for h in self.his:
+            import scipy.sparse as sp
+            A = sp.csr_matrix(h.adj_i_host); A.sort_indices()
+            rp.append(A.indptr[1:].astype(np.int64) + z); ci.append(A.indices.astype(np.int32)); z += A.nnz
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dtype=dt)
+        host = dict(ext_off=ext_off, link_off=link_off, comp_off=comp_off,
+                    maps_ol_el=cat([h.maps_ol_el_host for h in self.his], np.int32),
+                    maps_on_el=cat([h.maps_on_el_host for h in self.his], np.int32),
+                    link_rates=cat([h.link_rates_host for h in self.his], np.float64),
+                    cf_degs=cat([h.cf_degs_host for h in self.his], np.float64),
+                    node_mu=cat([h.node_mu_host for h in self.his], np.float64),
+                    adj_rowptr=np.concatenate(rp).astype(np.int32), adj_colidx=cat(ci, np.int32))
+        self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in host.items()}
+        self.total_links, self.total_comp, self.total_ext = int(link_off[-1]), int(comp_off[-1]), int(ext_off[-1])
+        self.link_off, self.comp_off, self.ext_off = link_off, comp_off, ext_off
+        st = _lib.mho_head_t()
+        st.n_graphs, st.max_links = B, int(max([h.num_links for h in self.his] + [0]))
+        st.total_links, st.total_comp, st.total_adj_nnz = self.total_links, self.total_comp, int(z)
+        for k in ("ext_off", "link_off", "comp_off", "maps_ol_el", "maps_on_el", "link_rates", "cf_degs", "node_mu",
+                  "adj_rowptr", "adj_colidx"):
+            setattr(st, k, self.dev[k].data_ptr())
+        st.T = float(self.his[0].T) if self.his else 0.0
+        self.struct, self._C, self._lib = st, C, _lib
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, lam, save=True):
+        """lam: float32 device tensor [total_ext] or [total_ext, 1] -> (link_delay [L], node_delay [nc]) fp64."""
+        lam = lam.reshape(-1).contiguous()
+        assert lam.dtype == torch.float32 and lam.numel() == self.total_ext
+        ld = torch.empty(self.total_links, dtype=torch.float64, device=self.device)
+        nd = torch.empty(self.total_comp, dtype=torch.float64, device=self.device)
+        self.saved_mu = torch.empty(11 * max(self.total_links, 1), dtype=torch.float64, device=self.device) if save else None
+        rc = self.ctx.lib.mho_queue_head_forward(self.ctx.handle, self._C.byref(self.struct), lam.data_ptr(), ld.data_ptr(),
+                                                 nd.data_ptr(), self.saved_mu.data_ptr() if save else None, self._stream())
+        self._lib.check(rc, "mho_queue_head_forward")
+        self.lam = lam
+        return ld, nd
+
+    def backward(self, g_link, g_node):
+        """gradients wrt (link_delay, node_delay) fp64 -> g_lam float32 [total_ext, 1]."""
+        g_link = g_link.reshape(-1).to(torch.float64).contiguous()
+        g_node = g_node.reshape(-1).to(torch.float64).contiguous()
+        g_lam = torch.empty(self.total_ext, dtype=torch.float32, device=self.device)
+        rc = self.ctx.lib.mho_queue_head_backward(self.ctx.handle, self._C.byref(self.struct), self.lam.data_ptr(),
+                                                  self.saved_mu.data_ptr(), g_link.data_ptr(), g_node.data_ptr(),
+                                                  g_lam.data_ptr(), self._stream())
+        self._lib.check(rc, "mho_queue_head_backward")
+        return g_lam.reshape(-1, 1)

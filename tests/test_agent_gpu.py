@@ -116,3 +116,37 @@ def test_replay_and_checkpoint_roundtrip_on_device(agent, tmp_path):
     back = tf_bundle.load_weights(tf_bundle.latest_checkpoint(str(tmp_path / "m")))
     flat = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for W, b in back])
     np.testing.assert_array_equal(flat, w1)   # fp64 master weights survive bit for bit
+
+
+def test_fused_queue_head_kernels_match_golden(golden_dir):
+    """mho_queue_head_forward / _backward (fp64) vs the oracle's head on the golden cases, batched 6 graphs at once."""
+    import torch
+    import chebnet_oracle as O
+    from multihop_offload_b200 import _lib
+    from multihop_offload_b200 import queue_head as qh
+    ctx = _lib.Context.get(0)
+    cases = [np.load(f) for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz")))]
+    his, sizes, lams = [], [], []
+    for z in cases:
+        obj, env = stub_case(z)
+        his.append(qh.HeadInputs(obj, env, None)); sizes.append(z["X"].shape[0]); lams.append(z["lam"][:, 0])
+    hb = qh.HeadBatch(his, sizes, ctx, "cuda:0")
+    lam = torch.as_tensor(np.concatenate(lams).astype(np.float32)).cuda()
+    ld, nd = hb.forward(lam, save=True)
+    ld, nd = ld.cpu().numpy(), nd.cpu().numpy()
+    rng = np.random.default_rng(0)
+    g_link = rng.normal(size=ld.shape); g_node = rng.normal(size=nd.shape)
+    g_lam = hb.backward(torch.as_tensor(g_link).cuda(), torch.as_tensor(g_node).cuda()).cpu().numpy()[:, 0]
+    for gi, z in enumerate(cases):
+        L = len(z["link_rates"])
+        Ai = sp.csr_matrix((z["adj_i_vals"], z["adj_i_colidx"], z["adj_i_rowptr"]), shape=(L, L))
+        lam32 = z["lam"].astype(np.float32).astype(np.float64)   # the kernels see the fp32 GNN output
+        rld, rnd, hc = O.queue_head_forward(lam32, z["maps_ol_el"], z["maps_on_el"], z["link_rates"], z["cf_degs"],
+                                            z["proc_bws"], Ai, int(z["T"]), return_cache=True)
+        a, b = hb.link_off[gi], hb.link_off[gi + 1]
+        c, d = hb.comp_off[gi], hb.comp_off[gi + 1]
+        np.testing.assert_allclose(ld[a:b], rld[:, 0], rtol=1e-12)
+        np.testing.assert_allclose(nd[c:d], rnd[:, 0], rtol=1e-12)
+        want = O.queue_head_vjp(hc, g_link[a:b], g_node[c:d], lam32.shape[0], z["maps_ol_el"], z["maps_on_el"])[:, 0]
+        e0, e1 = hb.ext_off[gi], hb.ext_off[gi + 1]
+        assert np.abs(g_lam[e0:e1] - want).max() <= 2e-7 * max(np.abs(want).max(), 1e-30)   # fp32 output
