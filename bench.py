@@ -50,14 +50,23 @@ def ba_csr(n, seed):
     return indptr, (np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64))
 
 
-def make_workload(n_graphs, rank=0, fixed_n=None, K=5, F=32):
+def make_workload(n_graphs, rank=0, fixed_n=None, K=5, F=32, pack=True):
     rng = np.random.default_rng(0 + 7919 * rank)
     sizes = np.full(n_graphs, fixed_n) if fixed_n else rng.choice(SIZES, size=n_graphs)
+    if pack and not fixed_n:
+        # same multiset of graphs, laid out in tile-packing order (first-fit decreasing): the order of independent
+        # graph instances in a batch is the batch builder's choice
+        from multihop_offload_b200.batch import pack_order
+        perm = pack_order(sizes, 128)
+        seeds = (1000 + np.arange(n_graphs) + 100003 * rank)[perm]
+        sizes = sizes[perm]
+    else:
+        seeds = 1000 + np.arange(n_graphs) + 100003 * rank
     goff = np.zeros(n_graphs + 1, dtype=np.int64)
     rps, cis = [np.zeros(1, dtype=np.int64)], []
     noff = zoff = 0
     for i, n in enumerate(sizes):
-        ip, ci = ba_csr(int(n), 1000 + i + 100003 * rank)
+        ip, ci = ba_csr(int(n), int(seeds[i]))
         rps.append(ip[1:] + zoff)
         cis.append(ci + noff)
         noff += int(n); zoff += ci.size
@@ -159,7 +168,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    w = make_workload(args.graphs, 0, args.fixed_n)
+    w = make_workload(args.graphs, 0, args.fixed_n, pack=not args.no_pack)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     ws = [(w["W"], w["b"])]
@@ -194,7 +203,8 @@ def workload_config(args, w):
                                                     "{%d}" % args.fixed_n if args.fixed_n else "{20..110 step 10}"),
             "graphs_per_gpu": args.graphs, "nodes_per_gpu": int(w["graph_off"][-1]), "nnz_per_gpu": int(w["rowptr"][-1]),
             "parallelism": "graph-instance sharding, no data-path collective",
-            "l2": "rotating over distinct input/output sets > 2x L2"}
+            "l2": "rotating over distinct input/output sets > 2x L2",
+            "batch_order": "graphs laid out in tile-packing order (first-fit decreasing, multihop_offload_b200.pack_order)"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -217,7 +227,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    w = make_workload(args.graphs, rank, args.fixed_n)
+    w = make_workload(args.graphs, rank, args.fixed_n, pack=not args.no_pack)
     net = ChebNet([LayerSpec(w["K"], w["F"], w["F"], 2, 0.2)], device=dev)
     net.set_weights([(w["W"], w["b"])])
     n_nodes = int(w["graph_off"][-1])
@@ -330,6 +340,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pack", action="store_true", help="keep the random graph order instead of tile-packing order")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:

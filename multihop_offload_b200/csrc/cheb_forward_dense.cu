@@ -1,0 +1,459 @@
+// ChebConv stack forward, all-tensor-core form (sm_100a, tcgen05 + TMEM) for batches of small graphs with a
+// BINARY adjacency (vals == NULL): replaces model([x_in, a_in]) of gnn_offloading_agent.py:149 (model of :81-123,
+// spektral ChebConv) for tiles of <= 128 nodes.
+//
+// A tile of packed graphs is at most 128 nodes, so its block of the operator fits one UMMA: the tile's adjacency is
+// expanded from CSR into a dense 128 x 128 bf16 matrix in shared memory (0/1 - exact in any format) and the sparse
+// recurrence becomes a tensor-core product.  The polynomial is evaluated with Clenshaw's recurrence, which needs
+// the input only once:
+//      P_k   = X W_k                         one UMMA, N = K * 32 columns of TMEM           (k = 0..K-1)
+//      B_K-1 = P_K-1
+//      B_k   = P_k + 2 A B_k+1 - B_k+2       UMMA accumulating A (2 B_k+1) straight onto P_k's TMEM columns
+//      out   = P_0 + A B_1 - B_2             (then bias, activation)
+// fp32 operands are carried through the bf16 tensor core as three bf16 parts (x = h + m + l exactly, 8 + 8 + 8
+// mantissa bits); 0/1 times a part is exact and TMEM accumulates in fp32, so the adjacency products are fp32-grade,
+// and X W keeps the six part products down to 2^-24 relative.  CUDA cores only move accumulators: per step each
+// thread reads its 8 TMEM values (row = TMEM lane, 8 columns), applies the recurrence with B_k+1 / B_k+2 held in
+// registers, splits the result into parts and stores three 16 B chunks.  No CSR walk, no row segments, no fixups.
+//
+// Shared memory per CTA (2 CTAs / SM): adjacency 32 KB, three part tiles 24 KB ([node][32 bf16], 64 B rows,
+// SWIZZLE_64B: A operand (K-major) of X W and B operand (MN-major) of A B with the same bytes), the bf16 weight
+// parts of every layer, two CSR staging sets.
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstring>
+
+#include "mho_common.cuh"
+#include "mho_internal.h"
+
+namespace {
+
+constexpr int DN_THREADS = 512;
+constexpr int DN_PART_BYTES = 128 * 64;  // one bf16 part tile: 128 nodes x 32 features
+constexpr int DN_ADJ_BYTES = 128 * 128 * 2;
+
+struct DenseParams {
+    BatchDev b;
+    int n_layers;
+    LayerDev layers[MHO_MAX_LAYERS];
+    const float* X;
+    float* Y;
+    float* saved;
+    const unsigned char* wimg;         // per layer: [part h][part m][part l] (n_rows x 64 B each) + 128 B bias row
+    int w_off[MHO_MAX_LAYERS];         // byte offset of each layer's block (multiples of 1024)
+    int w_bytes;
+    int nnz_cap;                       // staged colidx capacity (multiple of 4)
+    int need_adj;                      // some layer has K > 1
+    int tmem_cols;                     // power of two >= max_l K_l * nblk_l
+    int* sched;
+};
+
+__host__ __device__ inline int dn_nblk(int K, int f_out) { return K > 1 ? 32 : pad16(f_out); }
+__host__ __device__ inline int dn_layer_rows(int K, int f_out) { return K * dn_nblk(K, f_out); }
+__host__ __device__ inline int dn_layer_bytes(int K, int f_out) { return (3 * dn_layer_rows(K, f_out) * 64 + 128 + 1023) & ~1023; }
+
+// [rows][32 bf16] tile with 64 B rows, SWIZZLE_64B: 16 B chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+__device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t chunk) { return (row << 6) | ((chunk ^ ((row >> 1) & 3u)) << 4); }
+
+// x = h + m + l with three bf16 (exact for normal fp32): truncate, subtract, truncate, subtract
+__device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const uint32_t xb = __float_as_uint(x);
+    h = xb & 0xffff0000u;
+    const float r1 = x - __uint_as_float(h);
+    m = __float_as_uint(r1) & 0xffff0000u;
+    const float r2 = r1 - __uint_as_float(m);
+    l = __float_as_uint(r2) & 0xffff0000u;  // r2 has <= 8 significant bits: already a bf16
+}
+
+// eight fp32 -> one 16 B chunk per part, stored at (row, chunk) of the three part tiles
+__device__ __forceinline__ void store_parts(uint32_t parts_a, uint32_t row, uint32_t chunk, const float (&v)[8]) {
+    uint32_t h[8], m[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split3(v[i], h[i], m[i], l[i]);
+    const uint32_t off = sw64_off(row, chunk);
+    // bf16 pairs: element 2j in the low half
+#define MHO_PACK(p, j) ((p[2 * (j)] >> 16) | (p[2 * (j) + 1] & 0xffff0000u))
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + off), "r"(MHO_PACK(h, 0)), "r"(MHO_PACK(h, 1)), "r"(MHO_PACK(h, 2)), "r"(MHO_PACK(h, 3)) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + DN_PART_BYTES + off), "r"(MHO_PACK(m, 0)), "r"(MHO_PACK(m, 1)), "r"(MHO_PACK(m, 2)), "r"(MHO_PACK(m, 3)) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + 2 * DN_PART_BYTES + off), "r"(MHO_PACK(l, 0)), "r"(MHO_PACK(l, 1)), "r"(MHO_PACK(l, 2)), "r"(MHO_PACK(l, 3)) : "memory");
+#undef MHO_PACK
+}
+
+// shared-memory operand descriptors (cute::UMMA::SmemDescriptor): start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout << 61
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {  // layout 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, M = 128
+__device__ __forceinline__ uint32_t idesc_bf16_m128(uint32_t n, uint32_t b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+struct PrepDenseParams {
+    int n_layers;
+    LayerDev layers[MHO_MAX_LAYERS];
+    int w_off[MHO_MAX_LAYERS];
+    unsigned char* out;
+};
+
+__global__ void prepare_dense_weights_kernel(const __grid_constant__ PrepDenseParams p) {
+    for (int l = blockIdx.y; l < p.n_layers; l += gridDim.y) {
+        const LayerDev& L = p.layers[l];
+        const int nblk = dn_nblk(L.K, L.f_out);
+        const int n_rows = L.K * nblk;
+        unsigned char* img = p.out + p.w_off[l];
+        const int total = n_rows * 32;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+            const int k = idx / (nblk * 32), rem = idx - k * nblk * 32;
+            const int f = rem / nblk, o = rem - f * nblk;  // o fastest: coalesced reads of W[k][f][.]
+            float w = 0.f;
+            if (f < L.f_in && o < L.f_out) w = __ldg(L.W + ((size_t)k * L.f_in + f) * L.f_out + o);
+            uint32_t h, m, lo;
+            split3(w, h, m, lo);
+            const uint32_t n = (uint32_t)(k * nblk + o);
+            const uint32_t off = sw64_off(n, (uint32_t)f >> 3) + ((uint32_t)f & 7u) * 2u;
+            *reinterpret_cast<uint16_t*>(img + off) = (uint16_t)(h >> 16);
+            *reinterpret_cast<uint16_t*>(img + (size_t)n_rows * 64 + off) = (uint16_t)(m >> 16);
+            *reinterpret_cast<uint16_t*>(img + (size_t)n_rows * 128 + off) = (uint16_t)(lo >> 16);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            float* bias = reinterpret_cast<float*>(img + (size_t)n_rows * 192);
+            bias[threadIdx.x] = (L.b != nullptr && (int)threadIdx.x < L.f_out) ? __ldg(L.b + threadIdx.x) : 0.f;
+        }
+    }
+}
+
+struct TileInfoD { int node0, rows, nz0, nnz; };
+__device__ __forceinline__ TileInfoD load_tile(const BatchDev& b, int i) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(b.tile_info) + i);
+    return TileInfoD{v.x, v.y, v.z, v.w};
+}
+
+__device__ __forceinline__ void issue_csr_loads(const DenseParams& p, const TileInfoD& t, uint32_t rp_a, uint32_t ci_a, int tid) {
+    for (int i = tid; i <= t.rows; i += DN_THREADS) cp_async4(rp_a + i * 4, p.b.rowptr + t.node0 + i);
+    for (int e = tid; e < t.nnz; e += DN_THREADS) cp_async4(ci_a + e * 4, p.b.colidx + t.nz0 + e);
+}
+
+__global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_constant__ DenseParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // ---- shared memory carve-up
+    unsigned char* adj_s = smem;
+    unsigned char* parts_s = adj_s + (p.need_adj ? DN_ADJ_BYTES : 0);
+    unsigned char* w_s = parts_s + 3 * DN_PART_BYTES;
+    int* csr0 = reinterpret_cast<int*>(w_s + p.w_bytes);
+    const int rp_words = (128 + 2 + 3) & ~3;
+    const int csr_words = rp_words + p.nnz_cap;
+    int* s_idx = csr0 + 2 * csr_words;
+    const uint32_t adj_a = smem_u32(adj_s), parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
+    const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
+
+    // thread <-> accumulator element: TMEM lane = tile row; warp w may touch lane quadrant (w & 3); column block w >> 2
+    const int q = warp & 3, cb = warp >> 2;
+    const uint32_t r = (uint32_t)(q * 32 + lane);
+    const int c0 = cb * 8;
+
+    if (warp == 0) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
+    if (tid == 0) mbar_init(mbar, 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_idx + 4);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t mma_phase = 0;
+
+    // from here on global memory written by earlier launches in the stream is read
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int c = tid; c < p.w_bytes / 16; c += DN_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
+
+    // ---- dynamic tile scheduler (largest tile first; the last CTA out re-arms the counters)
+    if (tid == 0) { s_idx[0] = atomicAdd(p.sched, 1); s_idx[1] = atomicAdd(p.sched, 1); }
+    __syncthreads();
+    int i_cur = s_idx[0], i_nxt = s_idx[1];
+    __syncthreads();
+    auto finish = [&]() {
+        cp_async_wait<0>();
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+        }
+    };
+    if (i_cur >= p.b.n_tiles) { finish(); return; }
+    TileInfoD cur = load_tile(p.b, i_cur);
+    bool has_nxt = i_nxt < p.b.n_tiles;
+    TileInfoD nxt = cur;
+    if (has_nxt) nxt = load_tile(p.b, i_nxt);
+    issue_csr_loads(p, cur, csr_a0, csr_a0 + rp_words * 4, tid);
+    cp_async_commit();
+    int cs = 0;
+
+    const int fi0 = p.layers[0].f_in;
+    for (int it = 0;; ++it) {
+        const int* rp_s = csr0 + cs * csr_words;
+        const int* ci_s = rp_s + rp_words;
+        const int rows = cur.rows, node0 = cur.node0, nz0 = cur.nz0;
+        const bool live = (int)r < rows;
+
+        // this tile's input rows: 8 features per thread straight from global memory
+        float xin[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xin[j] = 0.f;
+        if (live) {
+            const float* src = p.X + (size_t)(node0 + (int)r) * fi0 + c0;
+            if ((fi0 & 3) == 0 && c0 + 8 <= fi0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w; xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < fi0) xin[j] = __ldg(src + j);
+            }
+        }
+        if (tid == 0) s_idx[it & 1] = has_nxt ? atomicAdd(p.sched, 1) : p.b.n_tiles;  // index of tile it+2
+        if (has_nxt) {
+            const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
+            issue_csr_loads(p, nxt, rp_n, rp_n + rp_words * 4, tid);
+        }
+        cp_async_commit();
+        // clear the adjacency (every UMMA that read it has completed: the previous tile's epilogue waited for them)
+        if (p.need_adj) {
+#pragma unroll
+            for (int i = 0; i < DN_ADJ_BYTES / 16 / DN_THREADS; ++i)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(adj_a + (uint32_t)(i * DN_THREADS + tid) * 16u), "r"(0u) : "memory");
+        }
+        store_parts(parts_a, r, (uint32_t)cb, xin);
+        cp_async_wait<1>();  // this tile's CSR slice (and the weights) have landed; the next tile's may still fly
+        __syncthreads();
+        const int i_nn = s_idx[it & 1];
+        const bool has_nn = has_nxt && i_nn < p.b.n_tiles;
+        TileInfoD nn = nxt;
+        if (has_nn) nn = load_tile(p.b, i_nn);
+
+        if (p.need_adj) {
+            // CSR -> dense 0/1 (duplicates add up): four threads per row, bf16x2 reductions into shared memory
+            const int row = tid >> 2;
+            if (row < rows) {
+                const int e1 = rp_s[row + 1] - nz0;
+                const uint32_t rbase = adj_a + ((uint32_t)row << 7);
+                const uint32_t rkey = (uint32_t)row & 7u;
+                for (int e = rp_s[row] - nz0 + (tid & 3); e < e1; e += 4) {
+                    const uint32_t col = (uint32_t)(ci_s[e] - node0);
+                    const uint32_t a = rbase + ((col >> 6) << 14) + (((((col & 63u) >> 3) ^ rkey)) << 4) + ((col & 6u) << 1);
+                    const uint32_t one = (col & 1u) ? 0x3F800000u : 0x00003F80u;
+                    asm volatile("red.shared.add.noftz.bf16x2 [%0], %1;" ::"r"(a), "r"(one) : "memory");
+                }
+            }
+        }
+
+        for (int li = 0; li < p.n_layers; ++li) {
+            const LayerDev& L = p.layers[li];
+            const int K = L.K;
+            const int nblk = dn_nblk(K, L.f_out);
+            const int n_rows = K * nblk;
+            const uint32_t w_l = w_a + (uint32_t)p.w_off[li];
+            const float* bias_s = reinterpret_cast<const float*>(w_s + p.w_off[li] + (size_t)n_rows * 192);
+
+            // ---- P = X_l [W_0 | ... | W_K-1]: six part products, two 16-wide K steps each
+            fence_proxy_async();  // part tiles / adjacency / cp.async-written weights -> tensor-core proxy
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = idesc_bf16_m128((uint32_t)n_rows, 0u);
+                const uint64_t a0 = desc_sw64(parts_a, 16, 512);
+                const uint64_t b0 = desc_sw64(w_l, 16, 512);
+                const uint64_t a_step = (uint64_t)(DN_PART_BYTES >> 4), b_step = (uint64_t)((n_rows * 64) >> 4);
+                // smallest terms first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h)
+                const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};
+                uint32_t accum = 0u;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        umma_bf16(tmem_base, a0 + a_step * pa[t] + 2 * ks, b0 + b_step * pb[t] + 2 * ks, idesc, accum);
+                        accum = 1u;
+                    }
+                }
+                umma_commit(mbar);
+            }
+            mbar_wait(mbar, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+
+            float b1[8], b2[8];
+            uint32_t v[8];
+            tmem_ld_32x32b_x8(tmem_row + (uint32_t)((K - 1) * nblk + c0), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { b1[j] = __uint_as_float(v[j]); b2[j] = 0.f; }
+            if (c0 >= nblk) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b1[j] = 0.f;
+            }
+
+            // ---- Clenshaw steps: D_k (+)= A (2 B_k+1)  [k >= 1],  D_0 (+)= A B_1
+            for (int k = K - 2; k >= 0; --k) {
+                float s[8];
+                const float f = k > 0 ? 2.f : 1.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] = f * b1[j];
+                store_parts(parts_a, r, (uint32_t)cb, s);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t idesc = idesc_bf16_m128(32u, 1u);
+                    const uint64_t a0 = umma_desc_sw128(adj_a);          // K-major, 128 B rows: two 64-column halves of 16 KB
+                    const uint64_t b0 = desc_sw64(parts_a, 8192, 512);   // MN-major: 8 node rows per 512 B group
+                    const uint32_t d = tmem_base + (uint32_t)(k * 32);
+#pragma unroll
+                    for (int part = 2; part >= 0; --part) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint64_t ad = a0 + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
+                            const uint64_t bd = b0 + (uint64_t)((part * DN_PART_BYTES + ks * 1024) >> 4);
+                            umma_bf16(d, ad, bd, idesc, 1u);
+                        }
+                    }
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, mma_phase);
+                mma_phase ^= 1u;
+                tc_fence_after();
+                tmem_ld_32x32b_x8(tmem_row + (uint32_t)(k * 32 + c0), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float bk = __uint_as_float(v[j]) - b2[j];
+                    b2[j] = b1[j];
+                    b1[j] = bk;
+                }
+            }
+
+            // ---- epilogue: bias + activation; last layer -> Y, hidden layer -> part tiles of the next layer (+ saved)
+            const bool last = (li == p.n_layers - 1);
+            const int fo = L.f_out;
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool on = live && (c0 + j < fo);
+                y[j] = on ? apply_act(b1[j] + bias_s[(c0 + j) & 31], L.act, L.slope) : 0.f;
+            }
+            float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
+            if (gout != nullptr && live && c0 < fo) {
+                float* dst = gout + (size_t)(node0 + (int)r) * fo + c0;
+                if ((fo & 3) == 0 && c0 + 8 <= fo) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < fo) dst[j] = y[j];
+                }
+            }
+            if (!last) store_parts(parts_a, r, (uint32_t)cb, y);
+        }
+
+        if (!has_nxt) break;
+        tc_fence_before();
+        __syncthreads();  // every TMEM read of this tile is done before the next tile's UMMAs overwrite the columns
+        cs ^= 1;
+        cur = nxt; nxt = nn; has_nxt = has_nn;
+    }
+    finish();
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, int max_tile_rows, int max_tile_nnz,
+                         int max_smem_optin) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg & 32) return false;  // MHO_DEBUG & 32: keep the CSR-walk kernel
+    if (has_vals || max_tile_rows > 128) return false;
+    int wb = 0;
+    bool need_adj = false;
+    for (int l = 0; l < n_layers; ++l) {
+        if (layers[l].f_in > 32 || layers[l].f_out > 32 || layers[l].K < 1) return false;
+        if (dn_layer_rows(layers[l].K, layers[l].f_out) > 256) return false;
+        wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
+        need_adj |= layers[l].K > 1;
+    }
+    const size_t smem = (size_t)(need_adj ? DN_ADJ_BYTES : 0) + 3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 64;
+    return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
+}
+
+int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off) {
+    int wb = 0;
+    for (int l = 0; l < n_layers; ++l) { w_off[l] = wb; wb += dn_layer_bytes(layers[l].K, layers[l].f_out); }
+    return wb;
+}
+
+cudaError_t prepare_dense_weights_launch(const LayerDev* layers, int n_layers, const int* w_off, unsigned char* out, cudaStream_t st) {
+    PrepDenseParams p;
+    p.n_layers = n_layers;
+    for (int l = 0; l < n_layers; ++l) { p.layers[l] = layers[l]; p.w_off[l] = w_off[l]; }
+    p.out = out;
+    dim3 grid(8, n_layers);
+    prepare_dense_weights_kernel<<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, const int* w_off, int w_bytes, int max_tile_nnz,
+                              int num_sms, cudaStream_t st) {
+    DenseParams p;
+    memset(&p, 0, sizeof(p));
+    p.b = fp.b;
+    p.n_layers = fp.n_layers;
+    int cols = 32;
+    for (int l = 0; l < fp.n_layers; ++l) {
+        p.layers[l] = fp.layers[l];
+        p.w_off[l] = w_off[l];
+        p.need_adj |= fp.layers[l].K > 1 ? 1 : 0;
+        const int n = dn_layer_rows(fp.layers[l].K, fp.layers[l].f_out);
+        while (cols < n) cols <<= 1;
+    }
+    p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
+    p.wimg = wimg; p.w_bytes = w_bytes;
+    p.nnz_cap = (max_tile_nnz + 3) & ~3;
+    p.tmem_cols = cols;
+    p.sched = fp.sched;
+    const size_t smem = (size_t)(p.need_adj ? DN_ADJ_BYTES : 0) + 3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 64;
+    static int smem_set[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((int)smem > smem_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(cheb_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[dev & 63] = (int)smem;
+    }
+    int grid = num_sms * 2;
+    if (grid > p.b.n_tiles) grid = p.b.n_tiles;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(DN_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, cheb_dense_kernel, p);
+}

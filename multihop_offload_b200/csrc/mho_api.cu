@@ -63,6 +63,7 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     cudaSetDevice(c->device);
     for (auto& s : c->scratch) if (s.ptr) cudaFree(s.ptr);
     if (c->wprep) cudaFree(c->wprep);
+    if (c->wdense) cudaFree(c->wdense);
     if (c->sched) cudaFree(c->sched);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
@@ -87,7 +88,7 @@ extern "C" int mho_host_free(void* ptr) {
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
 
 extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
-    if (c) c->wprep_valid = false;
+    if (c) { c->wprep_valid = false; c->wdense_valid = false; }
     return MHO_OK;
 }
 
@@ -114,6 +115,31 @@ static int ensure_prepared(mho_ctx* c, const mho_layer_t* layers, int n_layers, 
     c->wkey.clear();
     for (int l = 0; l < n_layers; ++l) c->wkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
     c->wprep_valid = true;
+    return MHO_OK;
+}
+
+static int ensure_prepared_dense(mho_ctx* c, const mho_layer_t* layers, int n_layers, const LayerDev* ld, cudaStream_t st) {
+    bool same = c->wdense_valid && (int)c->wdkey.size() == n_layers;
+    for (int l = 0; same && l < n_layers; ++l) {
+        mho_wkey k{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out};
+        same = (k == c->wdkey[l]);
+    }
+    if (same) return MHO_OK;
+    c->wd_bytes = cheb_dense_weight_bytes(layers, n_layers, c->wd_off);
+    const size_t bytes = (size_t)c->wd_bytes;
+    if (bytes > c->wdense_bytes) {
+        if (c->wdense) cudaFree(c->wdense);
+        c->wdense = nullptr; c->wdense_bytes = 0;
+        if (cudaMalloc((void**)&c->wdense, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
+        c->wdense_bytes = bytes;
+    }
+    if (cudaMemsetAsync(c->wdense, 0, bytes, st) != cudaSuccess) { mho_set_error("cudaMemsetAsync for prepared weights failed"); return MHO_ERR_CUDA; }
+    cudaError_t e = prepare_dense_weights_launch(ld, n_layers, c->wd_off, c->wdense, st);
+    if (e != cudaSuccess) { mho_set_error("prepare_dense_weights launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    c->wdkey.clear();
+    for (int l = 0; l < n_layers; ++l) c->wdkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
+    c->wdense_valid = true;
     return MHO_OK;
 }
 
@@ -242,10 +268,20 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.n_layers = n_layers;
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);
     p.X = X; p.Y = Y; p.saved = (float*)saved; p.total_nodes = b->total_nodes;
+    p.sched = c->sched;
+    // preferred: dense-adjacency tcgen05 path (binary adjacency, tiles <= 128 nodes, <= 32 features per layer)
+    if (b->tile_off && b->tile_info && c->sched &&
+        cheb_dense_eligible(layers, n_layers, b->vals != nullptr, b->max_tile_rows, b->max_tile_nnz, c->max_smem_optin)) {
+        rc = ensure_prepared_dense(c, layers, n_layers, p.layers, (cudaStream_t)stream);
+        if (rc) return rc;
+        cudaError_t e = cheb_dense_launch(p, c->wdense, c->wd_off, c->wd_bytes, b->max_tile_nnz, c->num_sms, (cudaStream_t)stream);
+        if (e != cudaSuccess) { mho_set_error("cheb_dense launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+        c->launches += 1;
+        return MHO_OK;
+    }
     rc = ensure_prepared(c, layers, n_layers, p.layers, (cudaStream_t)stream);
     if (rc) return rc;
     p.wprep = c->wprep;
-    p.sched = c->sched;
     for (int l = 0; l < n_layers; ++l) p.wprep_row_off[l] = c->wprep_row_off[l];
     bool too_large = false;
     cudaError_t e = cheb_forward_launch(p, b->max_tile_rows, b->max_tile_nnz, c->num_sms, c->max_smem_optin,

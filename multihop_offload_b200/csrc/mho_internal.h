@@ -28,6 +28,13 @@ struct mho_ctx {
     unsigned char* wprep = nullptr;
     size_t wprep_bytes = 0;
     int wprep_row_off[MHO_MAX_LAYERS] = {0};
+    // bf16-part weight images of the dense-adjacency tcgen05 path (cheb_forward_dense.cu), cached the same way
+    std::vector<mho_wkey> wdkey;
+    bool wdense_valid = false;
+    unsigned char* wdense = nullptr;
+    size_t wdense_bytes = 0;
+    int wd_off[MHO_MAX_LAYERS] = {0};
+    int wd_bytes = 0;
     int* sched = nullptr;  // two zero-initialised ints: dynamic tile scheduler state (self re-arming)
     int device = 0;
     int num_sms = 0;
@@ -45,5 +52,11 @@ void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, L
 int wprep_layer_rows(int K, int f_out);
 cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const int* row_off, unsigned char* out,
                                    cudaStream_t st);
+bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, int max_tile_rows, int max_tile_nnz,
+                         int max_smem_optin);
+int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off);
+cudaError_t prepare_dense_weights_launch(const LayerDev* layers, int n_layers, const int* w_off, unsigned char* out, cudaStream_t st);
+cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, const int* w_off, int w_bytes, int max_tile_nnz,
+                              int num_sms, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
                                 cudaStream_t st, bool* too_large);
