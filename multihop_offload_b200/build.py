@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB] + srcs + ["-lcudart"]
+    extra = ["-DMHO_PROBE"] if os.environ.get("MHO_PROBE") else []
+    cmd = [nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + srcs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

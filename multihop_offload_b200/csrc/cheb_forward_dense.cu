@@ -26,6 +26,13 @@
 #include "mho_common.cuh"
 #include "mho_internal.h"
 
+// -DMHO_PROBE: CTA 0 records clock64 marks of its first tile (thread 0 = UMMA issuer, thread 479 = a plain worker)
+#ifdef MHO_PROBE
+#define PROBE(id) do { if (blockIdx.x == 0 && it == 0 && (tid == 0 || tid == 479) && pn < 48) { pt[pn] = clock64(); pid[pn++] = (id); } } while (0)
+#else
+#define PROBE(id) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int DN_THREADS = 512;
@@ -141,20 +148,53 @@ __device__ __forceinline__ void issue_csr_loads(const DenseParams& p, const Tile
     for (int e = tid; e < t.nnz; e += DN_THREADS) cp_async4(ci_a + e * 4, p.b.colidx + t.nz0 + e);
 }
 
+// A operand straight from tensor memory (".ts" form): lane = row, 32-bit column = two consecutive bf16 of K
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void load_x_rows(const DenseParams& p, const TileInfoD& t, uint32_t r, int c0, float (&x)[8]) {
+    const int fi0 = p.layers[0].f_in;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if ((int)r < t.rows) {
+        const float* src = p.X + (size_t)(t.node0 + (int)r) * fi0 + c0;
+        if ((fi0 & 3) == 0 && c0 + 8 <= fi0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < fi0) x[j] = __ldg(src + j);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_constant__ DenseParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- shared memory carve-up
-    unsigned char* adj_s = smem;
-    unsigned char* parts_s = adj_s + (p.need_adj ? DN_ADJ_BYTES : 0);
+    unsigned char* parts_s = smem;
     unsigned char* w_s = parts_s + 3 * DN_PART_BYTES;
     int* csr0 = reinterpret_cast<int*>(w_s + p.w_bytes);
     const int rp_words = (128 + 2 + 3) & ~3;
     const int csr_words = rp_words + p.nnz_cap;
-    int* s_idx = csr0 + 2 * csr_words;
-    const uint32_t adj_a = smem_u32(adj_s), parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
+    int* s_idx = csr0 + 2 * csr_words;   // [0..1] first two tile indices, [2..3] mbarrier, [4] TMEM base, [8..12] next tile {index, info}
+    const uint32_t parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
 
     // thread <-> accumulator element: TMEM lane = tile row; warp w may touch lane quadrant (w & 3); column block w >> 2
@@ -169,6 +209,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_idx + 4);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t adj_col = (uint32_t)(p.tmem_cols - 64);  // the tile's adjacency: 128 lanes x 64 columns (bf16 pairs)
     uint32_t mma_phase = 0;
 
     // from here on global memory written by earlier launches in the stream is read
@@ -178,8 +219,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     // ---- dynamic tile scheduler (largest tile first; the last CTA out re-arms the counters)
     if (tid == 0) { s_idx[0] = atomicAdd(p.sched, 1); s_idx[1] = atomicAdd(p.sched, 1); }
     __syncthreads();
-    int i_cur = s_idx[0], i_nxt = s_idx[1];
-    __syncthreads();
+    const int i_cur = s_idx[0], i_nxt = s_idx[1];
     auto finish = [&]() {
         cp_async_wait<0>();
         tc_fence_before();
@@ -198,64 +238,50 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     issue_csr_loads(p, cur, csr_a0, csr_a0 + rp_words * 4, tid);
     cp_async_commit();
     int cs = 0;
+    float xin[8];
+    load_x_rows(p, cur, r, c0, xin);
 
-    const int fi0 = p.layers[0].f_in;
+#ifdef MHO_PROBE
+    long long pt[48]; int pid[48]; int pn = 0;
+#endif
     for (int it = 0;; ++it) {
+        PROBE(0);
         const int* rp_s = csr0 + cs * csr_words;
         const int* ci_s = rp_s + rp_words;
         const int rows = cur.rows, node0 = cur.node0, nz0 = cur.nz0;
         const bool live = (int)r < rows;
 
-        // this tile's input rows: 8 features per thread straight from global memory
-        float xin[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xin[j] = 0.f;
-        if (live) {
-            const float* src = p.X + (size_t)(node0 + (int)r) * fi0 + c0;
-            if ((fi0 & 3) == 0 && c0 + 8 <= fi0) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w; xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < fi0) xin[j] = __ldg(src + j);
-            }
-        }
-        if (tid == 0) s_idx[it & 1] = has_nxt ? atomicAdd(p.sched, 1) : p.b.n_tiles;  // index of tile it+2
+        // the scheduler's last thread fetches the index (and bounds) of tile it+2 in the background
+        int i_nn = p.b.n_tiles;
+        if (tid == DN_THREADS - 1 && has_nxt) i_nn = atomicAdd(p.sched, 1);
         if (has_nxt) {
             const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
             issue_csr_loads(p, nxt, rp_n, rp_n + rp_words * 4, tid);
         }
         cp_async_commit();
-        // clear the adjacency (every UMMA that read it has completed: the previous tile's epilogue waited for them)
-        if (p.need_adj) {
-#pragma unroll
-            for (int i = 0; i < DN_ADJ_BYTES / 16 / DN_THREADS; ++i)
-                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(adj_a + (uint32_t)(i * DN_THREADS + tid) * 16u), "r"(0u) : "memory");
-        }
         store_parts(parts_a, r, (uint32_t)cb, xin);
+        PROBE(1);
         cp_async_wait<1>();  // this tile's CSR slice (and the weights) have landed; the next tile's may still fly
         __syncthreads();
-        const int i_nn = s_idx[it & 1];
-        const bool has_nn = has_nxt && i_nn < p.b.n_tiles;
-        TileInfoD nn = nxt;
-        if (has_nn) nn = load_tile(p.b, i_nn);
+        PROBE(2);
 
         if (p.need_adj) {
-            // CSR -> dense 0/1 (duplicates add up): four threads per row, bf16x2 reductions into shared memory
-            const int row = tid >> 2;
-            if (row < rows) {
-                const int e1 = rp_s[row + 1] - nz0;
-                const uint32_t rbase = adj_a + ((uint32_t)row << 7);
-                const uint32_t rkey = (uint32_t)row & 7u;
-                for (int e = rp_s[row] - nz0 + (tid & 3); e < e1; e += 4) {
+            // CSR row -> 32 adjacency bits of this thread's (row, 32-column block) -> 16 bf16 pairs -> tensor memory
+            // (every UMMA that read the previous tile's adjacency has completed: its epilogue waited for them)
+            uint32_t mask = 0;
+            if (live) {
+                const int e1 = rp_s[r + 1] - nz0;
+                for (int e = rp_s[r] - nz0; e < e1; ++e) {
                     const uint32_t col = (uint32_t)(ci_s[e] - node0);
-                    const uint32_t a = rbase + ((col >> 6) << 14) + (((((col & 63u) >> 3) ^ rkey)) << 4) + ((col & 6u) << 1);
-                    const uint32_t one = (col & 1u) ? 0x3F800000u : 0x00003F80u;
-                    asm volatile("red.shared.add.noftz.bf16x2 [%0], %1;" ::"r"(a), "r"(one) : "memory");
+                    if ((int)(col >> 5) == cb) mask |= 1u << (col & 31u);
                 }
             }
+            uint32_t aw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) aw[j] = ((mask >> (2 * j)) & 1u) * 0x3F80u + ((mask >> (2 * j + 1)) & 1u) * 0x3F800000u;
+            tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
         }
+        PROBE(3);
 
         for (int li = 0; li < p.n_layers; ++li) {
             const LayerDev& L = p.layers[li];
@@ -265,8 +291,9 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             const uint32_t w_l = w_a + (uint32_t)p.w_off[li];
             const float* bias_s = reinterpret_cast<const float*>(w_s + p.w_off[li] + (size_t)n_rows * 192);
 
+            PROBE(4);
             // ---- P = X_l [W_0 | ... | W_K-1]: six part products, two 16-wide K steps each
-            fence_proxy_async();  // part tiles / adjacency / cp.async-written weights -> tensor-core proxy
+            fence_proxy_async();  // part tiles / cp.async-written weights -> tensor-core proxy
             tc_fence_before();
             __syncthreads();
             if (tid == 0) {
@@ -288,9 +315,13 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 }
                 umma_commit(mbar);
             }
+            PROBE(5);
+            // next tile's input rows ride behind the first layer's UMMAs
+            if (li == 0 && has_nxt) load_x_rows(p, nxt, r, c0, xin);
             mbar_wait(mbar, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
+            PROBE(6);
 
             float b1[8], b2[8];
             uint32_t v[8];
@@ -308,30 +339,34 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 const float f = k > 0 ? 2.f : 1.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s[j] = f * b1[j];
+                PROBE(10);
                 store_parts(parts_a, r, (uint32_t)cb, s);
                 fence_proxy_async();
                 tc_fence_before();
+                PROBE(11);
                 __syncthreads();
+                PROBE(12);
                 if (tid == 0) {
                     tc_fence_after();
                     const uint32_t idesc = idesc_bf16_m128(32u, 1u);
-                    const uint64_t a0 = umma_desc_sw128(adj_a);          // K-major, 128 B rows: two 64-column halves of 16 KB
                     const uint64_t b0 = desc_sw64(parts_a, 8192, 512);   // MN-major: 8 node rows per 512 B group
                     const uint32_t d = tmem_base + (uint32_t)(k * 32);
+                    const uint32_t a0 = tmem_base + adj_col;
 #pragma unroll
                     for (int part = 2; part >= 0; --part) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
-                            const uint64_t ad = a0 + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
                             const uint64_t bd = b0 + (uint64_t)((part * DN_PART_BYTES + ks * 1024) >> 4);
-                            umma_bf16(d, ad, bd, idesc, 1u);
+                            umma_bf16_ts(d, a0 + (uint32_t)(ks * 8), bd, idesc, 1u);
                         }
                     }
                     umma_commit(mbar);
                 }
+                PROBE(13);
                 mbar_wait(mbar, mma_phase);
                 mma_phase ^= 1u;
                 tc_fence_after();
+                PROBE(14);
                 tmem_ld_32x32b_x8(tmem_row + (uint32_t)(k * 32 + c0), v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -363,13 +398,25 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 }
             }
             if (!last) store_parts(parts_a, r, (uint32_t)cb, y);
+            PROBE(20);
         }
+#ifdef MHO_PROBE
+        if (blockIdx.x == 0 && it == 0 && (tid == 0 || tid == 479)) {
+            for (int i = 1; i < pn; ++i) printf("t%d id %d +%lld (abs %lld)\n", tid, pid[i], pt[i] - pt[i - 1], pt[i] - pt[0]);
+        }
+#endif
 
         if (!has_nxt) break;
+        if (tid == DN_THREADS - 1) {
+            s_idx[8] = i_nn;
+            if (i_nn < p.b.n_tiles) *reinterpret_cast<int4*>(s_idx + 12) = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + i_nn);
+        }
         tc_fence_before();
         __syncthreads();  // every TMEM read of this tile is done before the next tile's UMMAs overwrite the columns
         cs ^= 1;
-        cur = nxt; nxt = nn; has_nxt = has_nn;
+        cur = nxt;
+        has_nxt = s_idx[8] < p.b.n_tiles;
+        if (has_nxt) { const int4 v4 = *reinterpret_cast<const int4*>(s_idx + 12); nxt = TileInfoD{v4.x, v4.y, v4.z, v4.w}; }
     }
     finish();
 }
@@ -389,11 +436,11 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
     bool need_adj = false;
     for (int l = 0; l < n_layers; ++l) {
         if (layers[l].f_in > 32 || layers[l].f_out > 32 || layers[l].K < 1) return false;
-        if (dn_layer_rows(layers[l].K, layers[l].f_out) > 256) return false;
+        if (dn_layer_rows(layers[l].K, layers[l].f_out) + (layers[l].K > 1 ? 64 : 0) > 256) return false;  // TMEM: P + adjacency
         wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
         need_adj |= layers[l].K > 1;
     }
-    const size_t smem = (size_t)(need_adj ? DN_ADJ_BYTES : 0) + 3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 64;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 128;
     return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
 }
 
@@ -424,7 +471,9 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
         p.layers[l] = fp.layers[l];
         p.w_off[l] = w_off[l];
         p.need_adj |= fp.layers[l].K > 1 ? 1 : 0;
-        const int n = dn_layer_rows(fp.layers[l].K, fp.layers[l].f_out);
+    }
+    for (int l = 0; l < fp.n_layers; ++l) {
+        const int n = dn_layer_rows(fp.layers[l].K, fp.layers[l].f_out) + (p.need_adj ? 64 : 0);
         while (cols < n) cols <<= 1;
     }
     p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
@@ -432,7 +481,7 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     p.nnz_cap = (max_tile_nnz + 3) & ~3;
     p.tmem_cols = cols;
     p.sched = fp.sched;
-    const size_t smem = (size_t)(p.need_adj ? DN_ADJ_BYTES : 0) + 3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 64;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 128;
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
