@@ -165,6 +165,19 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 __device__ __forceinline__ void load_x_rows(const DenseParams& p, const TileInfoD& t, uint32_t r, int c0, float (&x)[8]) {
     const int fi0 = p.layers[0].f_in;
 #pragma unroll
@@ -271,9 +284,13 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             uint32_t mask = 0;
             if (live) {
                 const int e1 = rp_s[r + 1] - nz0;
-                for (int e = rp_s[r] - nz0; e < e1; ++e) {
-                    const uint32_t col = (uint32_t)(ci_s[e] - node0);
-                    if ((int)(col >> 5) == cb) mask |= 1u << (col & 31u);
+                for (int e = rp_s[r] - nz0; e < e1; e += 4) {  // four independent loads in flight (hub rows are long)
+                    uint32_t col[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) col[u] = (uint32_t)(ci_s[min(e + u, e1 - 1)] - node0);  // tail: repeats the last entry
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if ((int)(col[u] >> 5) == cb) mask |= 1u << (col[u] & 31u);
                 }
             }
             uint32_t aw[16];
@@ -333,14 +350,20 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 for (int j = 0; j < 8; ++j) b1[j] = 0.f;
             }
 
-            // ---- Clenshaw steps: D_k (+)= A (2 B_k+1)  [k >= 1],  D_0 (+)= A B_1
+            // ---- Clenshaw steps: D_k (+)= A (2 B_k+1)  [k >= 1],  D_0 (+)= A B_1.  One UMMA per 16 nodes covers the three
+            // parts at once (N = 96: the part tiles are three N-atoms, LBO apart): columns [32k, 32k+32) (+)= A h, the two
+            // blocks behind them - P_k+1 / P_k+2, consumed already and zeroed here - receive A m and A l.
+            const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             for (int k = K - 2; k >= 0; --k) {
                 float s[8];
                 const float f = k > 0 ? 2.f : 1.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s[j] = f * b1[j];
                 PROBE(10);
+                tmem_st_32x32b_x8(tmem_row + (uint32_t)((k + 1) * 32 + c0), zero8);
+                tmem_st_32x32b_x8(tmem_row + (uint32_t)((k + 2) * 32 + c0), zero8);
                 store_parts(parts_a, r, (uint32_t)cb, s);
+                tmem_wait_st();
                 fence_proxy_async();
                 tc_fence_before();
                 PROBE(11);
@@ -348,18 +371,12 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 PROBE(12);
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t idesc = idesc_bf16_m128(32u, 1u);
-                    const uint64_t b0 = desc_sw64(parts_a, 8192, 512);   // MN-major: 8 node rows per 512 B group
+                    const uint32_t idesc = idesc_bf16_m128(96u, 1u);
+                    const uint64_t b0 = desc_sw64(parts_a, DN_PART_BYTES, 512);   // MN-major: 8 node rows per 512 B group, N-atoms one part apart
                     const uint32_t d = tmem_base + (uint32_t)(k * 32);
                     const uint32_t a0 = tmem_base + adj_col;
 #pragma unroll
-                    for (int part = 2; part >= 0; --part) {
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const uint64_t bd = b0 + (uint64_t)((part * DN_PART_BYTES + ks * 1024) >> 4);
-                            umma_bf16_ts(d, a0 + (uint32_t)(ks * 8), bd, idesc, 1u);
-                        }
-                    }
+                    for (int ks = 0; ks < 8; ++ks) umma_bf16_ts(d, a0 + (uint32_t)(ks * 8), b0 + (uint64_t)((ks * 1024) >> 4), idesc, 1u);
                     umma_commit(mbar);
                 }
                 PROBE(13);
@@ -367,14 +384,19 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 mma_phase ^= 1u;
                 tc_fence_after();
                 PROBE(14);
-                tmem_ld_32x32b_x8(tmem_row + (uint32_t)(k * 32 + c0), v);
+                uint32_t v1[8], v2[8];
+                tmem_ld_32x32b_x8_nowait(tmem_row + (uint32_t)(k * 32 + c0), v);
+                tmem_ld_32x32b_x8_nowait(tmem_row + (uint32_t)((k + 1) * 32 + c0), v1);
+                tmem_ld_32x32b_x8_nowait(tmem_row + (uint32_t)((k + 2) * 32 + c0), v2);
+                tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float bk = __uint_as_float(v[j]) - b2[j];
+                    const float bk = (__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j]))) - b2[j];
                     b2[j] = b1[j];
                     b1[j] = bk;
                 }
             }
+            PROBE(15);
 
             // ---- epilogue: bias + activation; last layer -> Y, hidden layer -> part tiles of the next layer (+ saved)
             const bool last = (li == p.n_layers - 1);
@@ -385,6 +407,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 const bool on = live && (c0 + j < fo);
                 y[j] = on ? apply_act(b1[j] + bias_s[(c0 + j) & 31], L.act, L.slope) : 0.f;
             }
+            PROBE(16);
             float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
             if (gout != nullptr && live && c0 < fo) {
                 float* dst = gout + (size_t)(node0 + (int)r) * fo + c0;
@@ -436,7 +459,7 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
     bool need_adj = false;
     for (int l = 0; l < n_layers; ++l) {
         if (layers[l].f_in > 32 || layers[l].f_out > 32 || layers[l].K < 1) return false;
-        if (dn_layer_rows(layers[l].K, layers[l].f_out) + (layers[l].K > 1 ? 64 : 0) > 256) return false;  // TMEM: P + adjacency
+        if (dn_layer_rows(layers[l].K, layers[l].f_out) + (layers[l].K > 1 ? 96 : 0) > 256) return false;  // TMEM: P + a spare block + adjacency
         wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
         need_adj |= layers[l].K > 1;
     }
@@ -473,7 +496,7 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
         p.need_adj |= fp.layers[l].K > 1 ? 1 : 0;
     }
     for (int l = 0; l < fp.n_layers; ++l) {
-        const int n = dn_layer_rows(fp.layers[l].K, fp.layers[l].f_out) + (p.need_adj ? 64 : 0);
+        const int n = dn_layer_rows(fp.layers[l].K, fp.layers[l].f_out) + (p.need_adj ? 96 : 0);
         while (cols < n) cols <<= 1;
     }
     p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
