@@ -72,18 +72,25 @@ __device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32
     l = __float_as_uint(r2) & 0xffff0000u;  // r2 has <= 8 significant bits: already a bf16
 }
 
-// eight fp32 -> one 16 B chunk per part, stored at (row, chunk) of the three part tiles
+// eight fp32 -> one 16 B chunk per part, stored at (row, chunk) of the three part tiles.  A part is the upper half of
+// the fp32 word, so two neighbours pack with one byte permute; the remainders come from exact subtractions.
 __device__ __forceinline__ void store_parts(uint32_t parts_a, uint32_t row, uint32_t chunk, const float (&v)[8]) {
-    uint32_t h[8], m[8], l[8];
+    uint32_t ph[4], pm[4], pl[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split3(v[i], h[i], m[i], l[i]);
+    for (int j = 0; j < 4; ++j) {
+        const float x0 = v[2 * j], x1 = v[2 * j + 1];
+        ph[j] = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
+        const float r0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
+        const float r1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+        pm[j] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
+        const float q0 = r0 - __uint_as_float(__float_as_uint(r0) & 0xffff0000u);
+        const float q1 = r1 - __uint_as_float(__float_as_uint(r1) & 0xffff0000u);
+        pl[j] = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);  // <= 8 significant bits left: exact
+    }
     const uint32_t off = sw64_off(row, chunk);
-    // bf16 pairs: element 2j in the low half
-#define MHO_PACK(p, j) ((p[2 * (j)] >> 16) | (p[2 * (j) + 1] & 0xffff0000u))
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + off), "r"(MHO_PACK(h, 0)), "r"(MHO_PACK(h, 1)), "r"(MHO_PACK(h, 2)), "r"(MHO_PACK(h, 3)) : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + DN_PART_BYTES + off), "r"(MHO_PACK(m, 0)), "r"(MHO_PACK(m, 1)), "r"(MHO_PACK(m, 2)), "r"(MHO_PACK(m, 3)) : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + 2 * DN_PART_BYTES + off), "r"(MHO_PACK(l, 0)), "r"(MHO_PACK(l, 1)), "r"(MHO_PACK(l, 2)), "r"(MHO_PACK(l, 3)) : "memory");
-#undef MHO_PACK
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + off), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + DN_PART_BYTES + off), "r"(pm[0]), "r"(pm[1]), "r"(pm[2]), "r"(pm[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(parts_a + 2 * DN_PART_BYTES + off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
 }
 
 // shared-memory operand descriptors (cute::UMMA::SmemDescriptor): start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout << 61
@@ -209,6 +216,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     int* s_idx = csr0 + 2 * csr_words;   // [0..1] first two tile indices, [2..3] mbarrier, [4] TMEM base, [8..12] next tile {index, info}
     const uint32_t parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
+    uint2* lut_s = reinterpret_cast<uint2*>(s_idx + 16);                  // 4 adjacency bits -> two bf16 pairs
+    unsigned int* mask_s = reinterpret_cast<unsigned int*>(s_idx + 48);   // [128 rows][4] adjacency bits of the tile
+    if (tid < 16)
+        lut_s[tid] = make_uint2(((tid & 1) ? 0x3F80u : 0u) | ((tid & 2) ? 0x3F800000u : 0u), ((tid & 4) ? 0x3F80u : 0u) | ((tid & 8) ? 0x3F800000u : 0u));
 
     // thread <-> accumulator element: TMEM lane = tile row; warp w may touch lane quadrant (w & 3); column block w >> 2
     const int q = warp & 3, cb = warp >> 2;
@@ -273,29 +284,33 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
         }
         cp_async_commit();
         store_parts(parts_a, r, (uint32_t)cb, xin);
+        if (p.need_adj) mask_s[tid] = 0u;
         PROBE(1);
         cp_async_wait<1>();  // this tile's CSR slice (and the weights) have landed; the next tile's may still fly
         __syncthreads();
         PROBE(2);
 
         if (p.need_adj) {
-            // CSR row -> 32 adjacency bits of this thread's (row, 32-column block) -> 16 bf16 pairs -> tensor memory
+            // CSR -> 128 x 128 adjacency bits: one thread per stored entry (its row by bisection of the row pointers),
+            // then every thread expands the 32 bits of its (row, 32-column block) to 16 bf16 pairs in tensor memory
             // (every UMMA that read the previous tile's adjacency has completed: its epilogue waited for them)
-            uint32_t mask = 0;
-            if (live) {
-                const int e1 = rp_s[r + 1] - nz0;
-                for (int e = rp_s[r] - nz0; e < e1; e += 4) {  // four independent loads in flight (hub rows are long)
-                    uint32_t col[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) col[u] = (uint32_t)(ci_s[min(e + u, e1 - 1)] - node0);  // tail: repeats the last entry
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if ((int)(col[u] >> 5) == cb) mask |= 1u << (col[u] & 31u);
+            for (int e = tid; e < cur.nnz; e += DN_THREADS) {
+                const uint32_t col = (uint32_t)(ci_s[e] - node0);
+                int lo = 0, hi = rows - 1;  // largest row with rp[row] - nz0 <= e
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rp_s[mid] - nz0 <= e) lo = mid; else hi = mid - 1;
                 }
+                atomicOr(mask_s + lo * 4 + (col >> 5), 1u << (col & 31u));
             }
+            __syncthreads();
+            const uint32_t mask = mask_s[r * 4 + cb];
             uint32_t aw[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) aw[j] = ((mask >> (2 * j)) & 1u) * 0x3F80u + ((mask >> (2 * j + 1)) & 1u) * 0x3F800000u;
+            for (int j = 0; j < 8; ++j) {
+                const uint2 w = lut_s[(mask >> (4 * j)) & 15u];
+                aw[2 * j] = w.x; aw[2 * j + 1] = w.y;
+            }
             tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
         }
         PROBE(3);
@@ -403,9 +418,19 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             const int fo = L.f_out;
             float y[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool on = live && (c0 + j < fo);
-                y[j] = on ? apply_act(b1[j] + bias_s[(c0 + j) & 31], L.act, L.slope) : 0.f;
+            for (int j = 0; j < 8; ++j) y[j] = b1[j] + bias_s[(c0 + j) & 31];
+            if (L.act == MHO_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+            } else if (L.act == MHO_ACT_LEAKY) {
+                const float sl = L.slope;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : sl * y[j];
+            }
+            if (!live || c0 + 8 > fo) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (!live || c0 + j >= fo) y[j] = 0.f;
             }
             PROBE(16);
             float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
@@ -463,7 +488,7 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
         wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
         need_adj |= layers[l].K > 1;
     }
-    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 128;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 192 + 2048;
     return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
 }
 
@@ -504,7 +529,7 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     p.nnz_cap = (max_tile_nnz + 3) & ~3;
     p.tmem_cols = cols;
     p.sched = fp.sched;
-    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 128;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 192 + 2048;
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
