@@ -71,6 +71,11 @@ typedef struct {
     int32_t n_tiles;
     int32_t max_tile_rows;     /* max over tiles of the node count (host-known) */
     int32_t max_tile_nnz;      /* max over tiles of the nnz count (host-known) */
+    /* optional (device, 16 B aligned): the BINARY operator as bit rows, [total_nodes][4] words; bit j of word w of
+       node i = "i is adjacent to node tile_node0(i) + 32 w + j" (tile of the plan above, <= 128 nodes, from
+       mho_fill_adj_bits).  With it the forward's tensor-core path (vals == NULL, tiles <= 128 nodes) reads 16 B per
+       node instead of walking the CSR slice; NULL => the kernel derives the bits from rowptr/colidx itself. */
+    const uint32_t* adj_bits;
 } mho_batch_t;
 
 /* One ChebConv layer: Y = act(sum_k T_k(A) X W[k] + b), T_0=X, T_1=A X, T_k=2 A T_{k-1}-T_{k-2}
@@ -107,6 +112,11 @@ int mho_plan_tiles(const int32_t* graph_off_host, const int32_t* rowptr_host, in
 /* tile_info_host [n_tiles][4] from a plan (tile_off_host NULL => one graph per tile) */
 int mho_fill_tile_info(const int32_t* graph_off_host, const int32_t* rowptr_host, const int32_t* tile_off_host,
                        int32_t n_tiles, int32_t* tile_info_host);
+
+/* adj_bits_host [total_nodes][4] from a plan whose tiles have at most 128 nodes (see mho_batch_t.adj_bits);
+ * colidx_host holds GLOBAL node ids. */
+int mho_fill_adj_bits(const int32_t* graph_off_host, const int32_t* rowptr_host, const int32_t* colidx_host,
+                      const int32_t* tile_off_host, int32_t n_tiles, uint32_t* adj_bits_host);
 
 /* ---- forward: replaces ACOAgent.predict -> self.model([x_in, a_in])
  * (gnn_offloading_agent.py:144-150) for a whole batch.  X [total_nodes, layers[0].f_in],

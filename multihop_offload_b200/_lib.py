@@ -21,7 +21,7 @@ class mho_batch_t(C.Structure):
         ("graph_off", C.c_void_p), ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
         ("rowptr_t", C.c_void_p), ("colidx_t", C.c_void_p), ("vals_t", C.c_void_p),
         ("tile_off", C.c_void_p), ("tile_info", C.c_void_p), ("n_tiles", C.c_int32), ("max_tile_rows", C.c_int32),
-        ("max_tile_nnz", C.c_int32),
+        ("max_tile_nnz", C.c_int32), ("adj_bits", C.c_void_p),
     ]
 
 
@@ -54,6 +54,7 @@ PROTOTYPES = [
     ("mho_plan_tiles", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("mho_fill_tile_info", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ("mho_fill_adj_bits", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("mho_cheb_forward", C.c_int, [C.c_void_p, C.POINTER(mho_batch_t), C.POINTER(mho_layer_t), C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mho_saved_bytes", C.c_size_t, [C.POINTER(mho_batch_t), C.POINTER(mho_layer_t), C.c_int32]),

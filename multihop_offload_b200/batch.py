@@ -112,6 +112,14 @@ class GraphBatch:
                                           self.n_tiles, self.tile_info.ctypes.data), "mho_fill_tile_info")
         _lib.check(lib.mho_fill_tile_info(self.graph_off.ctypes.data, self.rowptr.ctypes.data, None,
                                           self.n_graphs, self.graph_info.ctypes.data), "mho_fill_tile_info")
+        # binary operator, tiles of <= 128 nodes: bit rows for the tensor-core forward (16 B per node)
+        self.adj_bits = None
+        if self.vals is None and self.n_tiles and self.max_tile_rows <= 128 and self.total_nodes:
+            bits = np.zeros((self.total_nodes, 4), dtype=np.uint32)
+            _lib.check(lib.mho_fill_adj_bits(self.graph_off.ctypes.data, self.rowptr.ctypes.data,
+                                             self.colidx.ctypes.data if self.total_nnz else None, self.tile_off.ctypes.data,
+                                             self.n_tiles, bits.ctypes.data), "mho_fill_adj_bits")
+            self.adj_bits = bits
         # largest tile first: the kernel's CTAs pull tiles in this order from a global counter
         if self.n_tiles > 1:
             cost = 3 * self.tile_info[:, 1].astype(np.int64) + self.tile_info[:, 3]
@@ -138,6 +146,8 @@ class GraphBatch:
                         tile_off=up(self.tile_off), tile_info=up(self.tile_info), graph_info=up(self.graph_info))
         if self.vals is not None:
             self.dev["vals"] = up(self.vals)
+        if getattr(self, "adj_bits", None) is not None:
+            self.dev["adj_bits"] = torch.from_numpy(self.adj_bits.view(np.int32)).to(device)
         if self.transpose is not None:
             self.dev["rowptr_t"], self.dev["colidx_t"], self.dev["vals_t"] = (up(a) for a in self.transpose)
         return self
@@ -173,6 +183,7 @@ class GraphBatch:
             b.tile_off, b.n_tiles = self.dev["tile_off"].data_ptr(), self.n_tiles
             b.tile_info = self.dev["tile_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_tile_rows, self.max_tile_nnz
+            b.adj_bits = self.dev["adj_bits"].data_ptr() if "adj_bits" in self.dev else None
         return b
 
     # ---- sharding across ranks (partition by graph, balanced by rows+nnz) ------

@@ -28,7 +28,10 @@
 
 // -DMHO_PROBE: CTA 0 records clock64 marks of its first tile (thread 0 = UMMA issuer, thread 479 = a plain worker)
 #ifdef MHO_PROBE
-#define PROBE(id) do { if (blockIdx.x == 0 && it == 0 && (tid == 0 || tid == 479) && pn < 48) { pt[pn] = clock64(); pid[pn++] = (id); } } while (0)
+#ifndef MHO_PROBE_IT
+#define MHO_PROBE_IT 1
+#endif
+#define PROBE(id) do { if (blockIdx.x == 0 && it == MHO_PROBE_IT && (tid == 0 || tid == 479) && pn < 48) { pt[pn] = clock64(); pid[pn++] = (id); } } while (0)
 #else
 #define PROBE(id) do { } while (0)
 #endif
@@ -50,6 +53,7 @@ struct DenseParams {
     int w_off[MHO_MAX_LAYERS];         // byte offset of each layer's block (multiples of 1024)
     int w_bytes;
     int nnz_cap;                       // staged colidx capacity (multiple of 4)
+    int stage_words;                   // words per operator staging set: 512 (bit rows) or 132 + nnz_cap (CSR slice)
     int need_adj;                      // some layer has K > 1
     int tmem_cols;                     // power of two >= max_l K_l * nblk_l
     int* sched;
@@ -150,7 +154,12 @@ __device__ __forceinline__ TileInfoD load_tile(const BatchDev& b, int i) {
     return TileInfoD{v.x, v.y, v.z, v.w};
 }
 
+// operator of one tile -> staging: the precomputed bit rows (16 B per node) when the batch carries them, else the CSR slice
 __device__ __forceinline__ void issue_csr_loads(const DenseParams& p, const TileInfoD& t, uint32_t rp_a, uint32_t ci_a, int tid) {
+    if (p.b.adj_bits != nullptr) {
+        if (tid < t.rows) cp_async16(rp_a + tid * 16, p.b.adj_bits + (size_t)(t.node0 + tid) * 4);
+        return;
+    }
     for (int i = tid; i <= t.rows; i += DN_THREADS) cp_async4(rp_a + i * 4, p.b.rowptr + t.node0 + i);
     for (int e = tid; e < t.nnz; e += DN_THREADS) cp_async4(ci_a + e * 4, p.b.colidx + t.nz0 + e);
 }
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     unsigned char* w_s = parts_s + 3 * DN_PART_BYTES;
     int* csr0 = reinterpret_cast<int*>(w_s + p.w_bytes);
     const int rp_words = (128 + 2 + 3) & ~3;
-    const int csr_words = rp_words + p.nnz_cap;
+    const int csr_words = p.stage_words;
     int* s_idx = csr0 + 2 * csr_words;   // [0..1] first two tile indices, [2..3] mbarrier, [4] TMEM base, [8..12] next tile {index, info}
     const uint32_t parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
@@ -240,10 +249,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int c = tid; c < p.w_bytes / 16; c += DN_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
 
-    // ---- dynamic tile scheduler (largest tile first; the last CTA out re-arms the counters)
-    if (tid == 0) { s_idx[0] = atomicAdd(p.sched, 1); s_idx[1] = atomicAdd(p.sched, 1); }
-    __syncthreads();
-    const int i_cur = s_idx[0], i_nxt = s_idx[1];
+    // ---- tile scheduler (dynamic from the third tile of a CTA on; the last CTA out re-arms the counters)
+    // the first two tiles of every CTA are static (no round trip to the counter before work starts); the counter
+    // hands out tiles 2 * gridDim.x onwards
+    const int i_cur = (int)blockIdx.x, i_nxt = (int)(blockIdx.x + gridDim.x);
     auto finish = [&]() {
         cp_async_wait<0>();
         tc_fence_before();
@@ -277,40 +286,59 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
 
         // the scheduler's last thread fetches the index (and bounds) of tile it+2 in the background
         int i_nn = p.b.n_tiles;
-        if (tid == DN_THREADS - 1 && has_nxt) i_nn = atomicAdd(p.sched, 1);
+        if (tid == DN_THREADS - 1 && has_nxt) i_nn = 2 * (int)gridDim.x + atomicAdd(p.sched, 1);
         if (has_nxt) {
             const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
             issue_csr_loads(p, nxt, rp_n, rp_n + rp_words * 4, tid);
         }
         cp_async_commit();
         store_parts(parts_a, r, (uint32_t)cb, xin);
-        if (p.need_adj) mask_s[tid] = 0u;
         PROBE(1);
         cp_async_wait<1>();  // this tile's CSR slice (and the weights) have landed; the next tile's may still fly
         __syncthreads();
         PROBE(2);
 
         if (p.need_adj) {
-            // CSR -> 128 x 128 adjacency bits: one thread per stored entry (its row by bisection of the row pointers),
-            // then every thread expands the 32 bits of its (row, 32-column block) to 16 bf16 pairs in tensor memory
+            // CSR -> 128 x 128 adjacency bits (four lanes per row), then every thread expands the 32 bits of its (row, 32-column block) to 16 bf16 pairs in tensor memory
             // (every UMMA that read the previous tile's adjacency has completed: its epilogue waited for them)
-            for (int e = tid; e < cur.nnz; e += DN_THREADS) {
-                const uint32_t col = (uint32_t)(ci_s[e] - node0);
-                int lo = 0, hi = rows - 1;  // largest row with rp[row] - nz0 <= e
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (rp_s[mid] - nz0 <= e) lo = mid; else hi = mid - 1;
+            if (p.b.adj_bits == nullptr) {
+                // four neighbouring lanes share a row: entries dealt round-robin, bits gathered in registers, OR-reduced
+                // across the four lanes with shuffles, lane s publishes word s
+                const int row = tid >> 2;
+                uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+                if (row < rows) {
+                    const int e1 = rp_s[row + 1] - nz0;
+#pragma unroll 2
+                    for (int e = rp_s[row] - nz0 + (tid & 3); e < e1; e += 4) {
+                        const uint32_t c = (uint32_t)(ci_s[e] - node0);
+                        const uint32_t bit = 1u << (c & 31u), w = c >> 5;
+                        m0 |= (w == 0u) ? bit : 0u;
+                        m1 |= (w == 1u) ? bit : 0u;
+                        m2 |= (w == 2u) ? bit : 0u;
+                        m3 |= (w == 3u) ? bit : 0u;
+                    }
                 }
-                atomicOr(mask_s + lo * 4 + (col >> 5), 1u << (col & 31u));
+#pragma unroll
+                for (int d = 1; d < 4; d <<= 1) {
+                    m0 |= __shfl_xor_sync(0xffffffffu, m0, d);
+                    m1 |= __shfl_xor_sync(0xffffffffu, m1, d);
+                    m2 |= __shfl_xor_sync(0xffffffffu, m2, d);
+                    m3 |= __shfl_xor_sync(0xffffffffu, m3, d);
+                }
+                const int sub = tid & 3;
+                mask_s[tid] = sub == 0 ? m0 : (sub == 1 ? m1 : (sub == 2 ? m2 : m3));  // word (row, sub); rows past the tile: 0
             }
-            __syncthreads();
-            const uint32_t mask = mask_s[r * 4 + cb];
+            PROBE(30);
+            if (p.b.adj_bits == nullptr) __syncthreads();
+            PROBE(31);
+            const uint32_t mask = p.b.adj_bits != nullptr ? (live ? (uint32_t)rp_s[r * 4 + cb] : 0u) : mask_s[r * 4 + cb];
             uint32_t aw[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint2 w = lut_s[(mask >> (4 * j)) & 15u];
                 aw[2 * j] = w.x; aw[2 * j + 1] = w.y;
             }
+            PROBE(32);
             tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
         }
         PROBE(3);
@@ -367,16 +395,18 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
 
             // ---- Clenshaw steps: D_k (+)= A (2 B_k+1)  [k >= 1],  D_0 (+)= A B_1.  One UMMA per 16 nodes covers the three
             // parts at once (N = 96: the part tiles are three N-atoms, LBO apart): columns [32k, 32k+32) (+)= A h, the two
-            // blocks behind them - P_k+1 / P_k+2, consumed already and zeroed here - receive A m and A l.
+            // blocks behind them - P_k+1 / P_k+2, consumed already and zeroed as soon as they were read - receive A m, A l.
             const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (K > 1) {
+                tmem_st_32x32b_x8(tmem_row + (uint32_t)((K - 1) * 32 + c0), zero8);
+                tmem_st_32x32b_x8(tmem_row + (uint32_t)(K * 32 + c0), zero8);
+            }
             for (int k = K - 2; k >= 0; --k) {
                 float s[8];
                 const float f = k > 0 ? 2.f : 1.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s[j] = f * b1[j];
                 PROBE(10);
-                tmem_st_32x32b_x8(tmem_row + (uint32_t)((k + 1) * 32 + c0), zero8);
-                tmem_st_32x32b_x8(tmem_row + (uint32_t)((k + 2) * 32 + c0), zero8);
                 store_parts(parts_a, r, (uint32_t)cb, s);
                 tmem_wait_st();
                 fence_proxy_async();
@@ -404,6 +434,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 tmem_ld_32x32b_x8_nowait(tmem_row + (uint32_t)((k + 1) * 32 + c0), v1);
                 tmem_ld_32x32b_x8_nowait(tmem_row + (uint32_t)((k + 2) * 32 + c0), v2);
                 tmem_wait_ld();
+                if (k > 0) {  // blocks k and k+1 are the next step's scratch: clear them while the recurrence computes
+                    tmem_st_32x32b_x8(tmem_row + (uint32_t)(k * 32 + c0), zero8);
+                    tmem_st_32x32b_x8(tmem_row + (uint32_t)((k + 1) * 32 + c0), zero8);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float bk = (__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j]))) - b2[j];
@@ -449,7 +483,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             PROBE(20);
         }
 #ifdef MHO_PROBE
-        if (blockIdx.x == 0 && it == 0 && (tid == 0 || tid == 479)) {
+        if (blockIdx.x == 0 && it == MHO_PROBE_IT && (tid == 0 || tid == 479)) {
             for (int i = 1; i < pn; ++i) printf("t%d id %d +%lld (abs %lld)\n", tid, pid[i], pt[i] - pt[i - 1], pt[i] - pt[0]);
         }
 #endif
@@ -527,9 +561,10 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
     p.wimg = wimg; p.w_bytes = w_bytes;
     p.nnz_cap = (max_tile_nnz + 3) & ~3;
+    p.stage_words = p.b.adj_bits != nullptr ? 512 : 132 + p.nnz_cap;
     p.tmem_cols = cols;
     p.sched = fp.sched;
-    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * (132 + p.nnz_cap) * 4 + 192 + 2048;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * p.stage_words * 4 + 192 + 2048;
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);

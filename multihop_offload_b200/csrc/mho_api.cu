@@ -222,6 +222,25 @@ static int validate_batch(const mho_batch_t* b, const char* who) {
     return MHO_OK;
 }
 
+extern "C" int mho_fill_adj_bits(const int32_t* goff, const int32_t* rowptr, const int32_t* colidx, const int32_t* tile_off,
+                                 int32_t n_tiles, uint32_t* out) {
+    if (!goff || !rowptr || !tile_off || !out || n_tiles < 0) { mho_set_error("mho_fill_adj_bits: invalid argument"); return MHO_ERR_INVALID; }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int n0 = goff[tile_off[t]], n1 = goff[tile_off[t + 1]];
+        if (n1 - n0 > 128) { mho_set_error("mho_fill_adj_bits: tile %d has %d nodes (> 128)", t, n1 - n0); return MHO_ERR_TOO_LARGE; }
+        for (int i = n0; i < n1; ++i) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+                const int c = colidx[e] - n0;
+                if (c < 0 || c >= n1 - n0) { mho_set_error("mho_fill_adj_bits: entry (%d,%d) leaves its tile", i, colidx[e]); return MHO_ERR_INVALID; }
+                w[c >> 5] |= 1u << (c & 31);
+            }
+            memcpy(out + (size_t)i * 4, w, sizeof(w));
+        }
+    }
+    return MHO_OK;
+}
+
 void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, LayerDev* out) {
     long long poff = 0, soff = 0;
     for (int l = 0; l < n_layers; ++l) {
@@ -264,6 +283,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.b.graph_off = b->graph_off; p.b.rowptr = b->rowptr; p.b.colidx = b->colidx; p.b.vals = b->vals;
     p.b.tile_off = b->tile_off; p.b.n_graphs = b->n_graphs;
     p.b.tile_info = b->tile_info;
+    p.b.adj_bits = b->adj_bits;
     p.b.n_tiles = b->tile_off ? b->n_tiles : b->n_graphs;
     p.n_layers = n_layers;
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);

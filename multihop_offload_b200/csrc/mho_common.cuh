@@ -232,6 +232,7 @@ struct BatchDev {
     const float* vals;
     const int32_t* tile_off;
     const int32_t* tile_info;  // optional [n_tiles][4] = {node0, rows, nz0, nnz}
+    const uint32_t* adj_bits;  // optional [total_nodes][4] binary operator as bit rows (tile-local columns)
     int n_tiles;
     int n_graphs;
 };
