@@ -211,6 +211,28 @@ __device__ __forceinline__ void load_x_rows(const DenseParams& p, const TileInfo
     }
 }
 
+// input rows of one tile -> the 16 KB staging tile ([row][32 fp32], 16 B chunks XOR-swizzled with row & 7), coalesced:
+// eight neighbouring lanes fetch one row.  Needs f_in % 4 == 0 (16 B chunks); chunks past f_in are never read.
+__device__ __forceinline__ void issue_x_loads(const DenseParams& p, const TileInfoD& t, uint32_t xs_a, int tid) {
+    const int fi0 = p.layers[0].f_in;
+    const int cpr = fi0 >> 2;  // 16 B chunks per row
+    const float* src = p.X + (size_t)t.node0 * fi0;
+    for (int i = tid; i < t.rows * 8; i += DN_THREADS) {
+        const uint32_t row = (uint32_t)i >> 3, ch = (uint32_t)i & 7u;
+        if ((int)ch < cpr) cp_async16(xs_a + (row << 7) + ((ch ^ (row & 7u)) << 4), src + (size_t)row * fi0 + ch * 4);
+    }
+}
+__device__ __forceinline__ void read_x_staged(const DenseParams& p, uint32_t xs_a, uint32_t r, int cb, bool live, float (&x)[8]) {
+    const int cpr = p.layers[0].f_in >> 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t ch = (uint32_t)(2 * cb + h);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && (int)ch < cpr) v = lds_f128(xs_a + (r << 7) + ((ch ^ (r & 7u)) << 4));
+        x[4 * h] = v.x; x[4 * h + 1] = v.y; x[4 * h + 2] = v.z; x[4 * h + 3] = v.w;
+    }
+}
+
 __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_constant__ DenseParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,6 +249,8 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
     uint2* lut_s = reinterpret_cast<uint2*>(s_idx + 16);                  // 4 adjacency bits -> two bf16 pairs
     unsigned int* mask_s = reinterpret_cast<unsigned int*>(s_idx + 48);   // [128 rows][4] adjacency bits of the tile
+    const uint32_t xs_a = smem_u32(s_idx + 48 + 512 + 208);               // 16 KB input staging (1024 B aligned: see the host side)
+    const bool x_staged = (p.layers[0].f_in & 3) == 0;
     if (tid < 16)
         lut_s[tid] = make_uint2(((tid & 1) ? 0x3F80u : 0u) | ((tid & 2) ? 0x3F800000u : 0u), ((tid & 4) ? 0x3F80u : 0u) | ((tid & 8) ? 0x3F800000u : 0u));
 
@@ -269,10 +293,9 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     TileInfoD nxt = cur;
     if (has_nxt) nxt = load_tile(p.b, i_nxt);
     issue_csr_loads(p, cur, csr_a0, csr_a0 + rp_words * 4, tid);
+    if (x_staged) issue_x_loads(p, cur, xs_a, tid);
     cp_async_commit();
     int cs = 0;
-    float xin[8];
-    load_x_rows(p, cur, r, c0, xin);
 
 #ifdef MHO_PROBE
     long long pt[48]; int pid[48]; int pn = 0;
@@ -287,15 +310,15 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
         // the scheduler's last thread fetches the index (and bounds) of tile it+2 in the background
         int i_nn = p.b.n_tiles;
         if (tid == DN_THREADS - 1 && has_nxt) i_nn = 2 * (int)gridDim.x + atomicAdd(p.sched, 1);
-        if (has_nxt) {
-            const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
-            issue_csr_loads(p, nxt, rp_n, rp_n + rp_words * 4, tid);
-        }
-        cp_async_commit();
-        store_parts(parts_a, r, (uint32_t)cb, xin);
-        PROBE(1);
-        cp_async_wait<1>();  // this tile's CSR slice (and the weights) have landed; the next tile's may still fly
+        cp_async_wait<0>();  // this tile's operator slice and input rows (and the weights) have landed
         __syncthreads();
+        PROBE(1);
+        {
+            float xin[8];
+            if (x_staged) read_x_staged(p, xs_a, r, cb, live, xin);
+            else load_x_rows(p, cur, r, c0, xin);
+            store_parts(parts_a, r, (uint32_t)cb, xin);
+        }
         PROBE(2);
 
         if (p.need_adj) {
@@ -376,8 +399,16 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 umma_commit(mbar);
             }
             PROBE(5);
-            // next tile's input rows ride behind the first layer's UMMAs
-            if (li == 0 && has_nxt) load_x_rows(p, nxt, r, c0, xin);
+            // the next tile's operator slice and input rows stream in behind the first layer's UMMAs (every thread
+            // has read the input staging tile: the barrier above)
+            if (li == 0) {
+                if (has_nxt) {
+                    const uint32_t rp_n = csr_a0 + (uint32_t)((cs ^ 1) * csr_words) * 4u;
+                    issue_csr_loads(p, nxt, rp_n, rp_n + rp_words * 4, tid);
+                    if (x_staged) issue_x_loads(p, nxt, xs_a, tid);
+                }
+                cp_async_commit();
+            }
             mbar_wait(mbar, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
@@ -468,7 +499,20 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             }
             PROBE(16);
             float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
-            if (gout != nullptr && live && c0 < fo) {
+            if (last && fo == 32) {
+                // through shared memory (the part tiles are free: every UMMA has completed) so that a warp writes four
+                // whole 128 B rows per instruction instead of 32 row fragments
+                sts_f128(parts_a + (r << 7) + (((uint32_t)(2 * cb) ^ (r & 7u)) << 4), make_float4(y[0], y[1], y[2], y[3]));
+                sts_f128(parts_a + (r << 7) + (((uint32_t)(2 * cb + 1) ^ (r & 7u)) << 4), make_float4(y[4], y[5], y[6], y[7]));
+                __syncthreads();
+                float* dst = gout + (size_t)node0 * 32;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t row = (uint32_t)(tid >> 3) + 64u * h, ch = (uint32_t)tid & 7u;
+                    if ((int)row < rows)
+                        *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = lds_f128(parts_a + (row << 7) + ((ch ^ (row & 7u)) << 4));
+                }
+            } else if (gout != nullptr && live && c0 < fo) {
                 float* dst = gout + (size_t)(node0 + (int)r) * fo + c0;
                 if ((fo & 3) == 0 && c0 + 8 <= fo) {
                     *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
@@ -522,7 +566,7 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
         wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
         need_adj |= layers[l].K > 1;
     }
-    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 192 + 2048;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 192 + 2048 + 832 + 16384;
     return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
 }
 
@@ -564,7 +608,7 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     p.stage_words = p.b.adj_bits != nullptr ? 512 : 132 + p.nnz_cap;
     p.tmem_cols = cols;
     p.sched = fp.sched;
-    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * p.stage_words * 4 + 192 + 2048;
+    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * p.stage_words * 4 + 192 + 2048 + 832 + 16384;
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
