@@ -306,14 +306,14 @@ def run_gpu_arm(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (fp32 storage/accumulate; dense products as split-TF32 on tcgen05, fp32-grade)", "data": "synthetic",
+            "dtype": "f32 (fp32 storage and accumulation; both products run on tcgen05 with operands split into three bf16 parts, fp32-grade)", "data": "synthetic",
             "config": workload_config(args, w),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "mho_cheb_forward_host (page-locked host buffers from mho_host_alloc; chunked upload/kernel/download pipeline)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "cheb_forward_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "cheb_dense_kernel",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes_survey_formula": alg_bytes + 4 * int(w["rowptr"][-1]),
                          "tflops_algorithmic": algorithmic_flops(w) / (per_launch_ms * 1e-3) / 1e12},
