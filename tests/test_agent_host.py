@@ -184,3 +184,32 @@ def test_adhoc_train_driver_replays_and_saves(agent_mod, tmp_path, monkeypatch):
     ck = tf_bundle.latest_checkpoint(os.path.join(F.modeldir, "model_ChebConv_BAT800_a5_c5_ACO_agent"))
     assert ck is not None and ck.endswith("cp-0000.ckpt")
     assert [W.shape for W, _ in tf_bundle.load_weights(ck)] == [(1, 4, 32), (1, 32, 32), (1, 32, 32), (1, 32, 32), (1, 32, 1)]
+
+
+def test_fill_adj_bits_and_pack_order():
+    """Host-side planning helpers of the tensor-core forward: bit rows == dense block, pack_order is a permutation
+    that never needs more tiles than the given order."""
+    import scipy.sparse as sp
+    from multihop_offload_b200 import GraphBatch, pack_order
+    rng = np.random.default_rng(5)
+    sizes = rng.choice(np.arange(20, 111, 10), size=60)
+    mats = []
+    for n in sizes:
+        a = (rng.random((n, n)) < 0.08).astype(np.float32)
+        a = np.triu(a, 1); a = a + a.T
+        mats.append(sp.csr_matrix(a))
+    b = GraphBatch.from_scipy(mats, tile_rows=128)
+    assert b.adj_bits is not None and b.adj_bits.shape == (b.total_nodes, 4)
+    for t in range(b.n_tiles):
+        n0, n1 = int(b.graph_off[b.tile_off[t]]), int(b.graph_off[b.tile_off[t + 1]])
+        dense = np.zeros((n1 - n0, 128), dtype=bool)
+        for i in range(n0, n1):
+            cols = b.colidx[b.rowptr[i]:b.rowptr[i + 1]] - n0
+            dense[i - n0, cols] = True
+        bits = np.unpackbits(b.adj_bits[n0:n1].view(np.uint8), axis=1, bitorder="little").astype(bool)
+        assert np.array_equal(bits, dense), t
+    perm = pack_order(sizes, 128)
+    assert sorted(perm.tolist()) == list(range(len(sizes)))
+    packed = GraphBatch.from_scipy([mats[i] for i in perm], tile_rows=128)
+    assert packed.n_tiles <= b.n_tiles
+    assert packed.max_tile_rows <= 128

@@ -217,3 +217,20 @@ def test_weights_change_is_picked_up(torch_cuda):
         net.set_weights(ws)
         Y = net.forward(batch, Xd).cpu().numpy()
         assert rel_err(Y, oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2), batch.graph_off) < TOL
+
+
+def test_dense_kernel_bit_rows_vs_csr_input(torch_cuda, golden_dir):
+    """The tensor-core forward takes the operator either as precomputed bit rows (mho_batch_t.adj_bits) or derives
+    the bits from the CSR slice in the kernel: same bits, same arithmetic -> identical results; both match the golden."""
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    z = np.load(os.path.join(golden_dir, "layer_K5_F32.npz"))
+    net = _net([LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)], [(z["W"], z["b"])])
+    X = torch_cuda.from_numpy(z["X"].astype(np.float32)).cuda()
+    batch = GraphBatch(z["graph_off"], z["rowptr"], z["colidx"], None, tile_rows=128, device="cuda:0")
+    assert "adj_bits" in batch.dev
+    Y_bits = net.forward(batch, X).cpu().numpy()
+    del batch.dev["adj_bits"]
+    batch._struct_cache = {}
+    Y_csr = net.forward(batch, X).cpu().numpy()
+    assert np.array_equal(Y_bits, Y_csr)
+    assert rel_err(Y_bits, z["Y"], z["graph_off"]) < TOL
