@@ -187,6 +187,16 @@ int mho_cheb_forward_host(mho_ctx_t* ctx, int32_t n_graphs, const int32_t* graph
                           const float* vals_host, const mho_layer_t* layers, int32_t n_layers,
                           const float* X_host, float* Y_host, mho_stream_t stream);
 
+/* Pipelined form: returns once everything is enqueued; *ticket identifies the call for mho_host_wait, which returns
+ * when Y_host of that call is complete.  At most two calls may be in flight per context (a third waits for the
+ * oldest), each with its own host buffers: the upload of call i+1 then overlaps the download of call i, keeping both
+ * PCIe directions busy.  Results of the GNN are identical to the blocking call. */
+int mho_cheb_forward_host_async(mho_ctx_t* ctx, int32_t n_graphs, const int32_t* graph_off_host,
+                                const int32_t* rowptr_host, const int32_t* colidx_host,
+                                const float* vals_host, const mho_layer_t* layers, int32_t n_layers,
+                                const float* X_host, float* Y_host, mho_stream_t stream, int32_t* ticket);
+int mho_host_wait(mho_ctx_t* ctx, int32_t ticket);
+
 /* Page-locked host staging buffers for the *_host call (cudaHostAlloc): measured on the round-1 box 54 GB/s
  * host->device against 16.5 GB/s from framework-pinned memory that ended up on the wrong NUMA node. */
 int mho_host_alloc(void** ptr, size_t bytes);

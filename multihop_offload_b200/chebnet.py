@@ -172,3 +172,22 @@ class ChebNet:
                                                 Y_host.ctypes.data, self._stream())
         _lib.check(rc, "mho_cheb_forward_host")
         return Y_host
+
+    def forward_host_async(self, graph_off, rowptr, colidx, vals, X_host, Y_host):
+        """Pipelined host-buffer call (mho_cheb_forward_host_async): returns a ticket right after enqueuing; Y_host is
+        complete after host_wait(ticket).  At most two calls in flight, each with its own (page-locked) host buffers;
+        the arrays must already be contiguous int32 / float32 (no hidden copies here: they would be freed too early)."""
+        for a, dt in ((graph_off, np.int32), (rowptr, np.int32), (colidx, np.int32), (X_host, np.float32), (Y_host, np.float32)):
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], "forward_host_async needs contiguous int32/float32 arrays"
+        assert vals is None or (vals.dtype == np.float32 and vals.flags["C_CONTIGUOUS"])
+        ticket = C.c_int32(-1)
+        rc = self.ctx.lib.mho_cheb_forward_host_async(self.ctx.handle, graph_off.size - 1, graph_off.ctypes.data,
+                                                      rowptr.ctypes.data, colidx.ctypes.data,
+                                                      vals.ctypes.data if vals is not None else None,
+                                                      self.layer_structs(), len(self.specs), X_host.ctypes.data,
+                                                      Y_host.ctypes.data, self._stream(), C.byref(ticket))
+        _lib.check(rc, "mho_cheb_forward_host_async")
+        return ticket.value
+
+    def host_wait(self, ticket):
+        _lib.check(self.ctx.lib.mho_host_wait(self.ctx.handle, int(ticket)), "mho_host_wait")

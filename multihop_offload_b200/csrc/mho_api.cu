@@ -67,7 +67,7 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     if (c->sched) cudaFree(c->sched);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
-        for (int i = 0; i < 2 * MHO_MAX_CHUNKS + 1; ++i) cudaEventDestroy(c->ev[i]);
+        for (int i = 0; i < 2 * MHO_EV_PER_SLOT; ++i) cudaEventDestroy(c->ev[i]);
     }
     delete c;
     return MHO_OK;
@@ -323,10 +323,13 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
 // downloads - so PCIe in, compute and PCIe out overlap; with pinned host buffers the step costs about
 // max(H2D, D2H) instead of their sum.  Global node / nnz offsets are kept (tile_info carries them), so a
 // chunk is just a slice of every array uploaded to its final place.
-extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
-                                     const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
-                                     int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream) {
+// Two calls may be in flight (mho_cheb_forward_host_async): each uses one of two device staging slots, so the upload
+// of call i+1 runs while call i computes and downloads - both PCIe directions busy at once.
+static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
+                             const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
+                             int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream, bool sync, int32_t* ticket) {
     if (!c || !goff_h || !rowptr_h || !X_h || !Y_h || n_graphs < 0) { mho_set_error("mho_cheb_forward_host: invalid argument"); return MHO_ERR_INVALID; }
+    if (ticket) *ticket = -1;
     int rc = validate_layers(layers, n_layers, "mho_cheb_forward_host");
     if (rc) return rc;
     if (n_graphs == 0) return MHO_OK;
@@ -373,7 +376,19 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
     const size_t b_x = (size_t)total_nodes * f_in * 4, b_y = (size_t)total_nodes * f_out * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total = al(b_rp) + al(b_ci) + al(b_va) + al(b_ti) + al(b_x) + al(b_y);
-    char* base = (char*)mho_scratch(c, 0, total);
+    const int slot = (int)(c->host_calls & 1);
+    c->host_calls += 1;
+    if (!c->h2d_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * MHO_EV_PER_SLOT; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    }
+    cudaEvent_t* ev = c->ev + slot * MHO_EV_PER_SLOT;
+    cudaEvent_t ev_start = ev[2 * MHO_MAX_CHUNKS], ev_done = ev[2 * MHO_MAX_CHUNKS + 1];
+    // the slot's previous user (two calls ago) must have finished its downloads before the buffers are recycled;
+    // growing the slot frees device memory, which waits for the device anyway
+    if (c->slot_used[slot]) CUDA_TRY(cudaEventSynchronize(ev_done));
+    char* base = (char*)mho_scratch(c, slot == 0 ? 0 : 4, total);
     if (!base) { mho_set_error("mho_cheb_forward_host: cudaMalloc of %zu B failed", total); return MHO_ERR_CUDA; }
     char* q = base;
     int32_t* d_rp = (int32_t*)q; q += al(b_rp);
@@ -383,15 +398,10 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
     float* d_x = (float*)q; q += al(b_x);
     float* d_y = (float*)q;
 
-    if (!c->h2d_stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2 * MHO_MAX_CHUNKS + 1; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
-    }
     cudaStream_t sh = c->h2d_stream, sd = c->d2h_stream;
-    // uploads start once the caller's stream reaches this point (previous users of the scratch are done)
-    CUDA_TRY(cudaEventRecord(c->ev[2 * MHO_MAX_CHUNKS], st));
-    CUDA_TRY(cudaStreamWaitEvent(sh, c->ev[2 * MHO_MAX_CHUNKS], 0));
+    // uploads may start as soon as the slot is free (checked above): they do NOT wait for the caller's stream, whose
+    // pending work is the other slot's kernels
+    (void)ev_start;
     CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
 
     // node / nnz extent of each chunk (tiles of a chunk are a contiguous run of graphs)
@@ -406,9 +416,9 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
         if (z1 > z0) CUDA_TRY(cudaMemcpyAsync(d_ci + z0, colidx_h + z0, (size_t)(z1 - z0) * 4, cudaMemcpyHostToDevice, sh));
         if (vals_h && z1 > z0) CUDA_TRY(cudaMemcpyAsync(d_va + z0, vals_h + z0, (size_t)(z1 - z0) * 4, cudaMemcpyHostToDevice, sh));
         CUDA_TRY(cudaMemcpyAsync(d_x + (size_t)n0 * f_in, X_h + (size_t)n0 * f_in, (size_t)(n1 - n0) * f_in * 4, cudaMemcpyHostToDevice, sh));
-        CUDA_TRY(cudaEventRecord(c->ev[k], sh));
+        CUDA_TRY(cudaEventRecord(ev[k], sh));
 
-        CUDA_TRY(cudaStreamWaitEvent(st, c->ev[k], 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev[k], 0));
         mho_batch_t b;
         memset(&b, 0, sizeof(b));
         b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
@@ -421,11 +431,37 @@ extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32
             rc = mho_cheb_forward(c, &b, layers, n_layers, d_x, d_y, nullptr, stream);
             if (rc) return rc;
         }
-        CUDA_TRY(cudaEventRecord(c->ev[MHO_MAX_CHUNKS + k], st));
-        CUDA_TRY(cudaStreamWaitEvent(sd, c->ev[MHO_MAX_CHUNKS + k], 0));
+        CUDA_TRY(cudaEventRecord(ev[MHO_MAX_CHUNKS + k], st));
+        CUDA_TRY(cudaStreamWaitEvent(sd, ev[MHO_MAX_CHUNKS + k], 0));
         CUDA_TRY(cudaMemcpyAsync(Y_h + (size_t)n0 * f_out, d_y + (size_t)n0 * f_out, (size_t)(n1 - n0) * f_out * 4, cudaMemcpyDeviceToHost, sd));
     }
-    CUDA_TRY(cudaStreamSynchronize(sd));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(ev_done, sd));
+    c->slot_used[slot] = true;
+    if (ticket) *ticket = slot;
+    if (sync) {
+        CUDA_TRY(cudaEventSynchronize(ev_done));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return MHO_OK;
+}
+
+extern "C" int mho_cheb_forward_host(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
+                                     const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
+                                     int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream) {
+    return forward_host_impl(c, n_graphs, goff_h, rowptr_h, colidx_h, vals_h, layers, n_layers, X_h, Y_h, stream, true, nullptr);
+}
+
+extern "C" int mho_cheb_forward_host_async(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff_h, const int32_t* rowptr_h,
+                                           const int32_t* colidx_h, const float* vals_h, const mho_layer_t* layers,
+                                           int32_t n_layers, const float* X_h, float* Y_h, mho_stream_t stream, int32_t* ticket) {
+    if (!ticket) { mho_set_error("mho_cheb_forward_host_async: ticket is NULL"); return MHO_ERR_INVALID; }
+    return forward_host_impl(c, n_graphs, goff_h, rowptr_h, colidx_h, vals_h, layers, n_layers, X_h, Y_h, stream, false, ticket);
+}
+
+extern "C" int mho_host_wait(mho_ctx_t* c, int32_t ticket) {
+    if (!c || ticket < 0 || ticket > 1) { mho_set_error("mho_host_wait: invalid ticket"); return MHO_ERR_INVALID; }
+    if (!c->slot_used[ticket]) return MHO_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev[ticket * MHO_EV_PER_SLOT + 2 * MHO_MAX_CHUNKS + 1]));
     return MHO_OK;
 }

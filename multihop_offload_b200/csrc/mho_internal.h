@@ -17,11 +17,14 @@ struct mho_wkey {
 };
 
 #define MHO_MAX_CHUNKS 8
+#define MHO_EV_PER_SLOT (2 * MHO_MAX_CHUNKS + 2)   // per staging slot: upload / kernel events per chunk, start, done
 
 struct mho_ctx {
     // pipelined host call: upload / download streams and per-chunk events
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev[2 * MHO_MAX_CHUNKS + 1] = {};
+    cudaEvent_t ev[2 * MHO_EV_PER_SLOT] = {};
+    int64_t host_calls = 0;          // host-buffer calls so far: call i uses staging slot i & 1
+    bool slot_used[2] = {false, false};
     // prepared-weight cache (see mho_invalidate_weights)
     std::vector<mho_wkey> wkey;
     bool wprep_valid = false;

@@ -234,3 +234,25 @@ def test_dense_kernel_bit_rows_vs_csr_input(torch_cuda, golden_dir):
     Y_csr = net.forward(batch, X).cpu().numpy()
     assert np.array_equal(Y_bits, Y_csr)
     assert rel_err(Y_bits, z["Y"], z["graph_off"]) < TOL
+
+
+def test_host_api_async_pipeline(torch_cuda):
+    """mho_cheb_forward_host_async / mho_host_wait: several calls through the two staging slots, each with its own
+    page-locked buffers and its own inputs, give exactly the blocking call's results."""
+    from multihop_offload_b200 import LayerSpec
+    from multihop_offload_b200._lib import PinnedArray, pinned_like
+    rng = np.random.default_rng(21)
+    mats = O.make_batch(rng.choice(np.arange(20, 111, 10), size=700), seed0=7000)
+    g_off, rowptr, colidx, vals = O.concat_batch(mats)
+    specs = [LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)]
+    net = _net(specs, random_weights(specs, rng, 0.5))
+    n = int(g_off[-1])
+    g, r, c = (pinned_like(np.ascontiguousarray(a, dtype=np.int32)) for a in (g_off, rowptr, colidx))
+    Xs = [pinned_like(rng.standard_normal((n, 32)).astype(np.float32)) for _ in range(5)]
+    Ys = [PinnedArray((n, 32), np.float32) for _ in range(5)]
+    refs = [net.forward_host(g.array, r.array, c.array, None, X.array).copy() for X in Xs]
+    tickets = [net.forward_host_async(g.array, r.array, c.array, None, Xs[i].array, Ys[i].array) for i in range(5)]
+    for t in tickets:
+        net.host_wait(t)
+    for i in range(5):
+        assert np.array_equal(Ys[i].array, refs[i]), i
