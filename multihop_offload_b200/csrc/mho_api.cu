@@ -346,8 +346,13 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     std::vector<int32_t> tinfo((size_t)n_tiles * 4 + 4);
     mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tinfo.data());
 
-    // chunks: contiguous runs of tiles of roughly equal bytes, at least ~192 tiles each, at most 8 chunks
-    int n_chunks = n_tiles / 192;
+    // chunks: contiguous runs of tiles of roughly equal bytes, ~300 tiles each (measured: copies of a few MB keep both
+    // PCIe directions efficient; 2 chunks beat 1, 3 and 4 for the 594-tile benchmark batch), at most 8 chunks
+    int n_chunks = (n_tiles + 150) / 300;
+    static int env_chunks = -1;
+    if (env_chunks < 0) { const char* e = getenv("MHO_CHUNKS"); env_chunks = e ? atoi(e) : 0; }  // tuning knob
+    if (env_chunks > 0) n_chunks = env_chunks;
+    if (n_chunks > n_tiles) n_chunks = n_tiles;
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > 8) n_chunks = 8;
     std::vector<int> cstart((size_t)n_chunks + 1, 0);
