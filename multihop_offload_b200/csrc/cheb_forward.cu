@@ -304,7 +304,7 @@ template <bool HAS_VALS, bool STAGED>
 __device__ __forceinline__ void issue_tile_loads(const FwdParams& p, const TileInfo& t, uint32_t Tbuf, uint32_t rp_a,
                                                  uint32_t pre_a, uint32_t val_a, int tid) {
     const int fi = p.layers[0].f_in;
-    if ((fi & 3) == 0) {
+    if ((fi & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0) {
         const int cpr = fi >> 2;  // 16 B chunks per row
         const float* src = p.X + (size_t)t.node0 * fi;
         const int total = t.rows * cpr;
@@ -658,7 +658,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                     }
                     if (gout != nullptr && r < rows) {
                         float* dst = gout + (size_t)(node0 + r) * fo + cb * 8;
-                        if ((fo & 3) == 0 && cb * 8 + 8 <= fo) {
+                        if ((fo & 3) == 0 && cb * 8 + 8 <= fo && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0) {
                             *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
                             *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
                         } else {
@@ -691,7 +691,7 @@ cheb_forward_kernel(const __grid_constant__ FwdParams p) {
                                 }
                                 if (gout != nullptr && r < rows) {
                                     float* dst = gout + (size_t)(node0 + r) * fo + col;
-                                    if ((fo & 1) == 0 && col + 1 < fo) {
+                                    if ((fo & 1) == 0 && col + 1 < fo && (reinterpret_cast<uintptr_t>(gout) & 7u) == 0) {
                                         *reinterpret_cast<float2*>(dst) = make_float2(y0, y1);
                                     } else {
                                         if (col < fo) dst[0] = y0;

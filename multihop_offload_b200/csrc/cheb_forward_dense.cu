@@ -200,7 +200,7 @@ __device__ __forceinline__ void load_x_rows(const DenseParams& p, const TileInfo
     for (int j = 0; j < 8; ++j) x[j] = 0.f;
     if ((int)r < t.rows) {
         const float* src = p.X + (size_t)(t.node0 + (int)r) * fi0 + c0;
-        if ((fi0 & 3) == 0 && c0 + 8 <= fi0) {
+        if ((fi0 & 3) == 0 && c0 + 8 <= fi0 && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
             x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
         } else {
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     uint2* lut_s = reinterpret_cast<uint2*>(s_idx + 16);                  // 4 adjacency bits -> two bf16 pairs
     unsigned int* mask_s = reinterpret_cast<unsigned int*>(s_idx + 48);   // [128 rows][4] adjacency bits of the tile
     const uint32_t xs_a = smem_u32(s_idx + 48 + 512 + 208);               // 16 KB input staging (1024 B aligned: see the host side)
-    const bool x_staged = (p.layers[0].f_in & 3) == 0;
+    const bool x_staged = (p.layers[0].f_in & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0;  // 16 B cp.async chunks
     if (tid < 16)
         lut_s[tid] = make_uint2(((tid & 1) ? 0x3F80u : 0u) | ((tid & 2) ? 0x3F800000u : 0u), ((tid & 4) ? 0x3F80u : 0u) | ((tid & 8) ? 0x3F800000u : 0u));
 
@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             }
             PROBE(16);
             float* gout = last ? p.Y : (p.saved ? p.saved + p.layers[li + 1].saved_off : nullptr);
-            if (last && fo == 32) {
+            const bool out16 = gout != nullptr && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;  // `saved` blocks start at odd offsets
+            if (last && fo == 32 && out16) {
                 // through shared memory (the part tiles are free: every UMMA has completed) so that a warp writes four
                 // whole 128 B rows per instruction instead of 32 row fragments
                 sts_f128(parts_a + (r << 7) + (((uint32_t)(2 * cb) ^ (r & 7u)) << 4), make_float4(y[0], y[1], y[2], y[3]));
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 }
             } else if (gout != nullptr && live && c0 < fo) {
                 float* dst = gout + (size_t)(node0 + (int)r) * fo + c0;
-                if ((fo & 3) == 0 && c0 + 8 <= fo) {
+                if (out16 && (fo & 3) == 0 && c0 + 8 <= fo) {
                     *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
                     *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
                 } else {

@@ -256,3 +256,32 @@ def test_host_api_async_pipeline(torch_cuda):
         net.host_wait(t)
     for i in range(5):
         assert np.array_equal(Ys[i].array, refs[i]), i
+
+
+def test_dense_kernel_edge_cases(torch_cuda):
+    """Tensor-core forward (binary operator, tiles <= 128 nodes): degenerate graphs, a full 128-node tile, a complete
+    graph (every adjacency bit set), unaligned / narrow feature widths, fused stacks with saved activations."""
+    from multihop_offload_b200 import GraphBatch, LayerSpec
+    rng = np.random.default_rng(77)
+    full = np.ones((128, 128)) - np.eye(128)
+    mats = [sp.csr_matrix((1, 1)), sp.csr_matrix(np.array([[0., 1.], [1., 0.]])), sp.csr_matrix((5, 5)),
+            O.ba_adjacency(128, 2, 11), sp.csr_matrix(full), O.ba_adjacency(3, 2, 1), O.ba_adjacency(127, 2, 12),
+            sp.csr_matrix((1, 1)), O.ba_adjacency(64, 2, 13), O.ba_adjacency(64, 2, 14)]
+    n = sum(m.shape[0] for m in mats)
+    for specs, scale in (([LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)], 0.05),
+                         ([LayerSpec(2, 7, 13, O.ACT_RELU), LayerSpec(3, 13, 32, O.ACT_NONE), LayerSpec(1, 32, 1, O.ACT_RELU)], 0.1),
+                         ([LayerSpec(4, 4, 32), LayerSpec(1, 32, 32), LayerSpec(5, 32, 8, O.ACT_RELU)], 0.05)):
+        ws = random_weights(specs, rng, scale)
+        net = _net(specs, ws)
+        X = rng.normal(size=(n, specs[0].f_in))
+        batch = GraphBatch.from_scipy(mats, tile_rows=128, device="cuda:0")
+        assert batch.adj_bits is not None and batch.max_tile_rows <= 128
+        Xd = torch_cuda.from_numpy(X.astype(np.float32)).cuda()
+        Y, saved = net.forward(batch, Xd, save=True)
+        ref, zscale = oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2, return_scale=True)
+        assert rel_err(Y.cpu().numpy(), ref, batch.graph_off, zscale) < TOL, [(s.K, s.f_in, s.f_out) for s in specs]
+        if len(specs) > 1:   # saved hidden activations = the next layer's inputs (what the VJP consumes)
+            acts = [s.act for s in specs]
+            h1 = oracle_batch_forward(mats, X, ws[:1], acts[:1], 0.2)
+            got = saved[: n * specs[1].f_in].view(n, specs[1].f_in).cpu().numpy()
+            assert rel_err(got, h1, batch.graph_off) < TOL
