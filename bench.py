@@ -294,6 +294,28 @@ def run_gpu_arm(args):
     h2d = int(Xh[0].array.nbytes + rp_h.array.nbytes + ci_h.array.nbytes)  # graph_off stays on the host (tile planning)
     d2h = int(Yh[0].array.nbytes)
 
+    # ---- second series: the reference's shipped 5-layer stack 4-32-32-32-32-1, K=1, on the same graphs
+    # (one fused launch per step; informational, not part of `value`)
+    from multihop_offload_b200 import reference_stack
+    rs = np.random.default_rng(5)
+    specs5 = reference_stack(K=1)
+    net5 = ChebNet(specs5, device=dev)
+    net5.set_weights([((rs.standard_normal((sp_.K, sp_.f_in, sp_.f_out)) * 0.2).astype(np.float32),
+                       np.zeros(sp_.f_out, np.float32)) for sp_ in specs5])
+    X5 = torch.randn((n_nodes, 4), device=dev)
+    Y5 = torch.empty((n_nodes, 1), dtype=torch.float32, device=dev)
+    for _ in range(5):
+        net5.forward(batches[0], X5, out=Y5)
+    barrier()
+    e5a, e5b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n5 = max(10, min(args.steps, 100))
+    e5a.record()
+    for i in range(n5):
+        net5.forward(batches[i % R], X5, out=Y5)
+    e5b.record()
+    barrier()
+    stack5_ms = e5a.elapsed_time(e5b) / n5
+
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +352,8 @@ def run_gpu_arm(args):
                          "algorithmic_bytes_survey_formula": alg_bytes + 4 * int(w["rowptr"][-1]),
                          "tflops_algorithmic": algorithmic_flops(w) / (per_launch_ms * 1e-3) / 1e12},
         }
+        out["series"] = {"reference_stack_4_32_32_32_32_1_K1": {
+            "value": args.graphs / (stack5_ms * 1e-3), "unit": "graph forwards/s per GPU (5 fused layers, rank 0)", "ms_per_step": stack5_ms}}
         if world == 1 and not args.no_cpu:
             v, cores, passes, dt = cpu_reference_rate(w, seconds=args.cpu_seconds, threads=1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -178,6 +178,16 @@ int mho_queue_head_forward(mho_ctx_t* ctx, const mho_head_t* head, const float* 
 int mho_queue_head_backward(mho_ctx_t* ctx, const mho_head_t* head, const float* lam, const double* saved_mu,
                             const double* g_link, const double* g_node, float* g_lam, mho_stream_t stream);
 
+/* ---- all-pairs shortest path lengths of a batch of small undirected graphs: replaces util.all_pairs_shortest_paths
+ * (src/util.py:101-110; call sites gnn_offloading_agent.py:286-287,304-305, AdHoc_test.py:135-136, AdHoc_train.py:134-135).
+ * The graphs are concatenated like a mho_batch_t: node_off [n_graphs+1], rowptr [total_nodes+1] (global offsets),
+ * colidx [nnz] GLOBAL node ids, both directions of every edge stored; weight [nnz] fp64 edge lengths (> 0, equal
+ * for the two directions) or NULL for hop counts.  dist receives one row-major n_g x n_g fp64 block per graph at element
+ * offset out_off[g] (out_off [n_graphs], int64); unreachable pairs are +inf (the reference raises KeyError there).
+ * Results are bit-identical to Dijkstra's algorithm on the same weights.  All pointers are DEVICE memory. */
+int mho_apsp(mho_ctx_t* ctx, int32_t n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx,
+             const double* weight, const int64_t* out_off, double* dist, mho_stream_t stream);
+
 /* ---- host-buffer convenience (the reference-facing call: numpy in, numpy out, as
  * ACOAgent.predict takes them).  All pointers are HOST memory (pinned for full speed); the
  * call uploads the batch + X, runs mho_cheb_forward, downloads Y and synchronises `stream`.

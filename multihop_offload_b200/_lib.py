@@ -73,6 +73,8 @@ PROTOTYPES = [
                                               C.POINTER(mho_layer_t), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.POINTER(C.c_int32)]),
     ("mho_host_wait", C.c_int, [C.c_void_p, C.c_int32]),
+    ("mho_apsp", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p]),
     ("mho_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     ("mho_host_free", C.c_int, [C.c_void_p]),
     ("mho_cheb_forward_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

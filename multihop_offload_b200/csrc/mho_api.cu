@@ -73,6 +73,17 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     return MHO_OK;
 }
 
+extern "C" int mho_apsp(mho_ctx_t* c, int32_t n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx,
+                        const double* weight, const int64_t* out_off, double* dist, mho_stream_t stream) {
+    if (!c || n_graphs < 0 || !node_off || !rowptr || !out_off || !dist) { mho_set_error("mho_apsp: invalid argument"); return MHO_ERR_INVALID; }
+    if (n_graphs == 0) return MHO_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = apsp_launch(n_graphs, node_off, rowptr, colidx, weight, out_off, dist, c->max_smem_optin, (cudaStream_t)stream);
+    if (e != cudaSuccess) { mho_set_error("apsp launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    return MHO_OK;
+}
+
 extern "C" int mho_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) { mho_set_error("mho_host_alloc: ptr is NULL"); return MHO_ERR_INVALID; }
     *ptr = nullptr;

@@ -61,5 +61,7 @@ int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off)
 cudaError_t prepare_dense_weights_launch(const LayerDev* layers, int n_layers, const int* w_off, unsigned char* out, cudaStream_t st);
 cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, const int* w_off, int w_bytes, int max_tile_nnz,
                               int num_sms, cudaStream_t st);
+cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
+                        const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
                                 cudaStream_t st, bool* too_large);

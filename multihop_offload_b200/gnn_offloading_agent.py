@@ -106,6 +106,15 @@ def _apsp():
         return all_pairs_shortest_paths
 
 
+def _apsp_or_none():
+    """On a CUDA device mho_apsp replaces util.all_pairs_shortest_paths; the reference checkout is only needed for
+    the environment (offloading_v3), so a missing util module is not an error there."""
+    try:
+        return _apsp()
+    except Exception:
+        return False
+
+
 class _Model(object):
     """Stand-in for the Keras model attribute: ``agent.model.trainable_weights`` / ``get_weights``."""
 
@@ -288,15 +297,31 @@ class ACOAgent:
             self._tape.update(lam64=lam64, link_delay=link_delay, node_delay=node_delay, hi=hi, hb=hb)
         return state, delay_mtx_ts, delay_mtx_np
 
+    def _on_gpu(self):
+        return str(self.device).startswith("cuda") and hasattr(self.net, "ctx")
+
+    def _shortest_paths(self, env, delay_mtx_np, cpu_apsp):
+        """sp_gnn / sp_hop of :286-287.  On a CUDA device: mho_apsp (bit-identical to the reference's Dijkstra); the CSR
+        of env.graph_c and the hop-count matrix depend on the topology only and are cached on the env object."""
+        if not self._on_gpu():
+            return cpu_apsp(env.graph_c, weight="delay"), cpu_apsp(env.graph_c, weight=None)
+        from .apsp import ApspPlan
+        plan = env.__dict__.get("_mho_apsp")
+        if plan is None or plan.n_edges != env.graph_c.number_of_edges():
+            plan = ApspPlan(env.graph_c, device=self.device, ctx=self.net.ctx)
+            plan.n_edges = env.graph_c.number_of_edges()
+            env.__dict__["_mho_apsp"] = plan
+        sp_gnn = plan.lengths(plan.entry_weights(delay_mtx_np))[0]
+        return sp_gnn, plan.hops()[0].copy()
+
     def forward_env(self, obj, env):
         """:278-291."""
-        all_pairs_shortest_paths = _apsp()
+        all_pairs_shortest_paths = _apsp_or_none() if self._on_gpu() else _apsp()
         state, delay_mtx_ts, delay_mtx_np = self.forward(obj, env)
         for (src, dst) in env.graph_c.edges:
             env.graph_c[src][dst]["delay"] = delay_mtx_np[src, dst]
         delay_servers = np.diagonal(delay_mtx_np)
-        sp_gnn = all_pairs_shortest_paths(env.graph_c, weight="delay")
-        sp_hop = all_pairs_shortest_paths(env.graph_c, weight=None)
+        sp_gnn, sp_hop = self._shortest_paths(env, delay_mtx_np, all_pairs_shortest_paths)
         np.fill_diagonal(sp_gnn, delay_servers)
         decisions, delay_est = env.offloading(sp_gnn, sp_hop)
         delay_links_gnn, delay_nodes_gnn, delay_unit_gnn = env.run()
@@ -312,13 +337,12 @@ class ACOAgent:
     def forward_backward(self, obj, env, explore=0.0):
         """:293-453 - forward, environment step, analytic critic, route gradient, VJP to the weights."""
         import torch
-        all_pairs_shortest_paths = _apsp()
+        all_pairs_shortest_paths = _apsp_or_none() if self._on_gpu() else _apsp()
         state, delay_mtx_ts, delay_mtx_np = self.forward(obj, env, save=True)
         for (src, dst) in env.graph_c.edges:
             env.graph_c[src][dst]["delay"] = delay_mtx_np[src, dst]
         delay_servers = np.diagonal(delay_mtx_np)
-        sp_gnn = all_pairs_shortest_paths(env.graph_c, weight="delay")
-        sp_hop = all_pairs_shortest_paths(env.graph_c, weight=None)
+        sp_gnn, sp_hop = self._shortest_paths(env, delay_mtx_np, all_pairs_shortest_paths)
         np.fill_diagonal(sp_gnn, delay_servers)
         decisions, delay_est = env.offloading(sp_gnn, sp_hop, explore)
         delay_links_gnn, delay_nodes_gnn, delay_unit_gnn = env.run()

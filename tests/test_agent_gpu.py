@@ -150,3 +150,21 @@ def test_fused_queue_head_kernels_match_golden(golden_dir):
         want = O.queue_head_vjp(hc, g_link[a:b], g_node[c:d], lam32.shape[0], z["maps_ol_el"], z["maps_on_el"])[:, 0]
         e0, e1 = hb.ext_off[gi], hb.ext_off[gi + 1]
         assert np.abs(g_lam[e0:e1] - want).max() <= 2e-7 * max(np.abs(want).max(), 1e-30)   # fp32 output
+
+
+def test_shortest_path_matrices_on_device_equal_dijkstra(agent, golden_dir):
+    """ACOAgent._shortest_paths (sp_gnn / sp_hop of gnn_offloading_agent.py:286-287) runs mho_apsp on a CUDA device:
+    bit-identical to Dijkstra on the delay matrix the agent just produced; the plan is cached per topology."""
+    import apsp_oracle as AO
+    f = sorted(glob.glob(os.path.join(golden_dir, "case*.npz")))[0]
+    z = np.load(f)
+    obj, env = stub_case(z)
+    state, D_ts, D_np = agent.forward(obj, env)
+    sp_gnn, sp_hop = agent._shortest_paths(env, D_np, None)
+    edges = list(env.graph_c.edges)
+    w = [D_np[a, b] for (a, b) in edges]
+    assert np.array_equal(sp_gnn, AO.apsp_lengths(env.num_nodes, edges, w))
+    assert np.array_equal(sp_hop, AO.apsp_lengths(env.num_nodes, edges, None))
+    plan = env.__dict__["_mho_apsp"]
+    agent._shortest_paths(env, D_np, None)
+    assert env.__dict__["_mho_apsp"] is plan
