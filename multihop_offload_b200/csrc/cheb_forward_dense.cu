@@ -3,8 +3,8 @@
 // spektral ChebConv) for tiles of <= 128 nodes.
 //
 // A tile of packed graphs is at most 128 nodes, so its block of the operator fits one UMMA: the tile's adjacency is
-// expanded from CSR into a dense 128 x 128 bf16 matrix in shared memory (0/1 - exact in any format) and the sparse
-// recurrence becomes a tensor-core product.  The polynomial is evaluated with Clenshaw's recurrence, which needs
+// expanded into a dense 128 x 128 bf16 matrix (0/1 - exact in any format) and the sparse recurrence becomes a
+// tensor-core product.  The polynomial is evaluated with Clenshaw's recurrence, which needs
 // the input only once:
 //      P_k   = X W_k                         one UMMA, N = K * 32 columns of TMEM           (k = 0..K-1)
 //      B_K-1 = P_K-1
@@ -16,9 +16,11 @@
 // thread reads its 8 TMEM values (row = TMEM lane, 8 columns), applies the recurrence with B_k+1 / B_k+2 held in
 // registers, splits the result into parts and stores three 16 B chunks.  No CSR walk, no row segments, no fixups.
 //
-// Shared memory per CTA (2 CTAs / SM): adjacency 32 KB, three part tiles 24 KB ([node][32 bf16], 64 B rows,
-// SWIZZLE_64B: A operand (K-major) of X W and B operand (MN-major) of A B with the same bytes), the bf16 weight
-// parts of every layer, two CSR staging sets.
+// The tile's adjacency lives in TENSOR MEMORY (A operand of the UMMA, 128 lanes x 64 columns of bf16 pairs, written with
+// tcgen05.st from 16 B of adjacency bits per node); the three part tiles ([node][32 bf16], 64 B rows, SWIZZLE_64B) are
+// at once the K-major A operand of X W and the MN-major B operand of A B (three N-atoms one LBO apart: one N = 96 UMMA
+// per 16 nodes covers the three parts).  Shared memory per CTA (2 CTAs / SM, tensor memory is the limit): part tiles
+// 24 KB, the bf16 weight parts of every layer, two operator staging sets, a 16 KB input staging tile.
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstring>
@@ -40,7 +42,6 @@ namespace {
 
 constexpr int DN_THREADS = 512;
 constexpr int DN_PART_BYTES = 128 * 64;  // one bf16 part tile: 128 nodes x 32 features
-constexpr int DN_ADJ_BYTES = 128 * 128 * 2;
 
 struct DenseParams {
     BatchDev b;

@@ -178,7 +178,7 @@ def test_full_size_linearity_property(torch_cuda):
 
 
 def test_host_api_multichunk_pipeline_equals_device_api(torch_cuda):
-    """1024 graphs -> ~600 tiles -> the host call runs as 3 pipelined chunks (upload / kernel / download
+    """1024 graphs -> ~600 tiles -> the host call runs as pipelined chunks of ~300 tiles (upload / kernel / download
     streams); the result must equal the single-launch device path bit for bit (same tiles, same order of
     floating-point operations inside every tile), with and without operator values."""
     from multihop_offload_b200 import GraphBatch, LayerSpec
