@@ -204,6 +204,7 @@ def workload_config(args, w):
             "graphs_per_gpu": args.graphs, "nodes_per_gpu": int(w["graph_off"][-1]), "nnz_per_gpu": int(w["rowptr"][-1]),
             "parallelism": "graph-instance sharding, no data-path collective",
             "l2": "rotating over distinct input/output sets > 2x L2",
+            "streams": "%d CUDA streams, one library context each; consecutive steps are independent batches and may overlap at their boundaries" % int(getattr(args, "streams", 1)),
             "batch_order": "graphs laid out in tile-packing order (first-fit decreasing, multihop_offload_b200.pack_order)"}
 
 
@@ -239,31 +240,57 @@ def run_gpu_arm(args):
     Xs = [X0] + [torch.randn_like(X0) for _ in range(R - 1)]
     Ys = [torch.empty((n_nodes, w["F"]), dtype=torch.float32, device=dev) for _ in range(R)]
 
+    # Steps are independent batches.  With --streams S (default 3) they are issued round-robin on S CUDA streams, each
+    # with its own library context (tile counters, weight images): stream order is kept inside a stream, and the tail
+    # of one step (the last tiles of its 2.007 rounds) overlaps the head of the next instead of idling 146 SMs
+    # (measured on B200: 22.8 / 22.1 / 19.6 us per step with 1 / 2 / 3 streams).
+    n_str = max(1, int(args.streams))
+    nets = [net]
+    for _ in range(n_str - 1):
+        n2 = ChebNet([LayerSpec(w["K"], w["F"], w["F"], 2, 0.2)], device=dev)
+        n2.set_weights([(w["W"], w["b"])])
+        nets.append(n2)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)] if n_str > 1 else [torch.cuda.current_stream(dev)]
+
     def step(i):
         j = i % R
-        net.forward(batches[j], Xs[j], out=Ys[j])
+        k = i % n_str
+        if n_str == 1:
+            nets[0].forward(batches[j], Xs[j], out=Ys[j])
+        else:
+            with torch.cuda.stream(streams[k]):
+                nets[k].forward(batches[j], Xs[j], out=Ys[j])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3) + n_str):
         step(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = net.ctx.launch_count()
+    l0 = sum(n_.ctx.launch_count() for n_ in nets)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    main = torch.cuda.current_stream(dev)
+    ev0.record(main)
+    if n_str > 1:
+        for s_ in streams:
+            s_.wait_event(ev0)
     for i in range(args.steps):
         step(i)
-    ev1.record()
+    if n_str > 1:
+        for s_ in streams:
+            done = torch.cuda.Event()
+            done.record(s_)
+            main.wait_event(done)
+    ev1.record(main)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = net.ctx.launch_count() - l0
+    launches = sum(n_.ctx.launch_count() for n_ in nets) - l0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers in, host buffers out, through the C-ABI host call
@@ -376,6 +403,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="independent steps are issued round-robin on this many CUDA streams")
     ap.add_argument("--no-pack", action="store_true", help="keep the random graph order instead of tile-packing order")
     args = ap.parse_args()
     if args.impl == "reference":

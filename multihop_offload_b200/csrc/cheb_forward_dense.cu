@@ -632,6 +632,8 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static int no_pdl = -1;
+    if (no_pdl < 0) { const char* e = getenv("MHO_NO_PDL"); no_pdl = e ? atoi(e) : 0; }
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, cheb_dense_kernel, p);
 }
