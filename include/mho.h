@@ -90,6 +90,8 @@ typedef struct {
 } mho_layer_t;
 
 /* ---- context ---------------------------------------------------------------------------- */
+/* A context owns the tile-scheduler counters, the packed weight images and the host-call staging slots: use it from ONE
+ * stream at a time (launches on one stream are ordered; for concurrent streams create one context per stream). */
 int mho_create(mho_ctx_t** ctx, int device);
 int mho_destroy(mho_ctx_t* ctx);
 const char* mho_last_error(void);

@@ -54,13 +54,16 @@ def glorot_uniform_(specs, rng):
 
 
 class ChebNet:
-    def __init__(self, specs, device="cuda:0", params=None, seed=0):
+    def __init__(self, specs, device="cuda:0", params=None, seed=0, private_context=False):
+        """private_context=True: this net gets its own mho_ctx_t (tile-scheduler counters, weight-image cache, staging
+        slots) instead of the per-device shared one - required when several nets / streams launch concurrently: a
+        context serialises nothing itself and must only be used from one stream at a time."""
         import torch
         self.specs = list(specs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.MhoError("ChebNet needs a CUDA device (no CPU fallback by design)")
-        self.ctx = _lib.Context.get(self.device.index or 0)
+        self.ctx = _lib.Context(self.device.index or 0) if private_context else _lib.Context.get(self.device.index or 0)
         self.n_params = int(sum(s.n_params for s in self.specs))
         if params is None:
             params = glorot_uniform_(self.specs, np.random.default_rng(seed))
