@@ -285,3 +285,30 @@ def test_dense_kernel_edge_cases(torch_cuda):
             h1 = oracle_batch_forward(mats, X, ws[:1], acts[:1], 0.2)
             got = saved[: n * specs[1].f_in].view(n, specs[1].f_in).cpu().numpy()
             assert rel_err(got, h1, batch.graph_off) < TOL
+
+
+def test_two_streams_two_contexts_equal_single_stream(torch_cuda, golden_dir):
+    """Independent batches on two CUDA streams, one private library context each (tile counters, weight images are
+    per context): the overlapped launches give exactly the results of launches issued one after the other."""
+    from multihop_offload_b200 import ChebNet, GraphBatch, LayerSpec
+    rng = np.random.default_rng(31)
+    z = np.load(os.path.join(golden_dir, "layer_K5_F32.npz"))
+    specs = [LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)]
+    nets = [ChebNet(specs, device="cuda:0", private_context=True) for _ in range(2)]
+    for n_ in nets:
+        n_.set_weights([(z["W"], z["b"])])
+    assert nets[0].ctx is not nets[1].ctx
+    mats = O.make_batch(rng.choice(np.arange(20, 111, 10), size=900), seed0=9000)
+    batch = GraphBatch.from_scipy(mats, device="cuda:0")
+    Xs = [torch_cuda.randn((batch.total_nodes, 32), device="cuda") for _ in range(6)]
+    want = [nets[0].forward(batch, X).clone() for X in Xs]
+    torch_cuda.cuda.synchronize()
+    streams = [torch_cuda.cuda.Stream() for _ in range(2)]
+    outs = [torch_cuda.empty_like(want[0]) for _ in Xs]
+    for rep in range(3):
+        for i, X in enumerate(Xs):
+            with torch_cuda.cuda.stream(streams[i & 1]):
+                nets[i & 1].forward(batch, X, out=outs[i])
+    torch_cuda.cuda.synchronize()
+    for i in range(len(Xs)):
+        assert torch_cuda.equal(outs[i], want[i]), i
