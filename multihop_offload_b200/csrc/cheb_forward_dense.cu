@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     if (x_staged) issue_x_loads(p, cur, xs_a, tid);
     cp_async_commit();
     int cs = 0;
+    cp_async_wait<0>();  // the first tile's operator slice and input rows, and the weights, have landed
+    __syncthreads();
 
 #ifdef MHO_PROBE
     long long pt[48]; int pid[48]; int pn = 0;
@@ -311,8 +313,6 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
         // the scheduler's last thread fetches the index (and bounds) of tile it+2 in the background
         int i_nn = p.b.n_tiles;
         if (tid == DN_THREADS - 1 && has_nxt) i_nn = 2 * (int)gridDim.x + atomicAdd(p.sched, 1);
-        cp_async_wait<0>();  // this tile's operator slice and input rows (and the weights) have landed
-        __syncthreads();
         PROBE(1);
         {
             float xin[8];
@@ -322,49 +322,6 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
         }
         PROBE(2);
 
-        if (p.need_adj) {
-            // CSR -> 128 x 128 adjacency bits (four lanes per row), then every thread expands the 32 bits of its (row, 32-column block) to 16 bf16 pairs in tensor memory
-            // (every UMMA that read the previous tile's adjacency has completed: its epilogue waited for them)
-            if (p.b.adj_bits == nullptr) {
-                // four neighbouring lanes share a row: entries dealt round-robin, bits gathered in registers, OR-reduced
-                // across the four lanes with shuffles, lane s publishes word s
-                const int row = tid >> 2;
-                uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
-                if (row < rows) {
-                    const int e1 = rp_s[row + 1] - nz0;
-#pragma unroll 2
-                    for (int e = rp_s[row] - nz0 + (tid & 3); e < e1; e += 4) {
-                        const uint32_t c = (uint32_t)(ci_s[e] - node0);
-                        const uint32_t bit = 1u << (c & 31u), w = c >> 5;
-                        m0 |= (w == 0u) ? bit : 0u;
-                        m1 |= (w == 1u) ? bit : 0u;
-                        m2 |= (w == 2u) ? bit : 0u;
-                        m3 |= (w == 3u) ? bit : 0u;
-                    }
-                }
-#pragma unroll
-                for (int d = 1; d < 4; d <<= 1) {
-                    m0 |= __shfl_xor_sync(0xffffffffu, m0, d);
-                    m1 |= __shfl_xor_sync(0xffffffffu, m1, d);
-                    m2 |= __shfl_xor_sync(0xffffffffu, m2, d);
-                    m3 |= __shfl_xor_sync(0xffffffffu, m3, d);
-                }
-                const int sub = tid & 3;
-                mask_s[tid] = sub == 0 ? m0 : (sub == 1 ? m1 : (sub == 2 ? m2 : m3));  // word (row, sub); rows past the tile: 0
-            }
-            PROBE(30);
-            if (p.b.adj_bits == nullptr) __syncthreads();
-            PROBE(31);
-            const uint32_t mask = p.b.adj_bits != nullptr ? (live ? (uint32_t)rp_s[r * 4 + cb] : 0u) : mask_s[r * 4 + cb];
-            uint32_t aw[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint2 w = lut_s[(mask >> (4 * j)) & 15u];
-                aw[2 * j] = w.x; aw[2 * j + 1] = w.y;
-            }
-            PROBE(32);
-            tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
-        }
         PROBE(3);
 
         for (int li = 0; li < p.n_layers; ++li) {
@@ -400,6 +357,51 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                 umma_commit(mbar);
             }
             PROBE(5);
+            // the tile's adjacency goes to tensor memory while the first layer's X W group runs (it is first read by the
+            // first Clenshaw step, behind that step's fence + barrier)
+            if (li == 0 && p.need_adj) {
+                    // CSR -> 128 x 128 adjacency bits (four lanes per row), then every thread expands the 32 bits of its (row, 32-column block) to 16 bf16 pairs in tensor memory
+                    // (every UMMA that read the previous tile's adjacency has completed: its epilogue waited for them)
+                    if (p.b.adj_bits == nullptr) {
+                        // four neighbouring lanes share a row: entries dealt round-robin, bits gathered in registers, OR-reduced
+                        // across the four lanes with shuffles, lane s publishes word s
+                        const int row = tid >> 2;
+                        uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+                        if (row < rows) {
+                            const int e1 = rp_s[row + 1] - nz0;
+#pragma unroll 2
+                            for (int e = rp_s[row] - nz0 + (tid & 3); e < e1; e += 4) {
+                                const uint32_t c = (uint32_t)(ci_s[e] - node0);
+                                const uint32_t bit = 1u << (c & 31u), w = c >> 5;
+                                m0 |= (w == 0u) ? bit : 0u;
+                                m1 |= (w == 1u) ? bit : 0u;
+                                m2 |= (w == 2u) ? bit : 0u;
+                                m3 |= (w == 3u) ? bit : 0u;
+                            }
+                        }
+#pragma unroll
+                        for (int d = 1; d < 4; d <<= 1) {
+                            m0 |= __shfl_xor_sync(0xffffffffu, m0, d);
+                            m1 |= __shfl_xor_sync(0xffffffffu, m1, d);
+                            m2 |= __shfl_xor_sync(0xffffffffu, m2, d);
+                            m3 |= __shfl_xor_sync(0xffffffffu, m3, d);
+                        }
+                        const int sub = tid & 3;
+                        mask_s[tid] = sub == 0 ? m0 : (sub == 1 ? m1 : (sub == 2 ? m2 : m3));  // word (row, sub); rows past the tile: 0
+                    }
+                    PROBE(30);
+                    if (p.b.adj_bits == nullptr) __syncthreads();
+                    PROBE(31);
+                    const uint32_t mask = p.b.adj_bits != nullptr ? (live ? (uint32_t)rp_s[r * 4 + cb] : 0u) : mask_s[r * 4 + cb];
+                    uint32_t aw[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint2 w = lut_s[(mask >> (4 * j)) & 15u];
+                        aw[2 * j] = w.x; aw[2 * j + 1] = w.y;
+                    }
+                    PROBE(32);
+                    tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
+                }
             // the next tile's operator slice and input rows stream in behind the first layer's UMMAs (every thread
             // has read the input staging tile: the barrier above)
             if (li == 0) {
@@ -539,8 +541,9 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             s_idx[8] = i_nn;
             if (i_nn < p.b.n_tiles) *reinterpret_cast<int4*>(s_idx + 12) = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + i_nn);
         }
+        cp_async_wait<0>();  // the next tile's operator slice and input rows have landed (issued a whole tile ago)
         tc_fence_before();
-        __syncthreads();  // every TMEM read of this tile is done before the next tile's UMMAs overwrite the columns
+        __syncthreads();  // ... and every TMEM read of this tile is done before the next tile's UMMAs overwrite the columns
         cs ^= 1;
         cur = nxt;
         has_nxt = s_idx[8] < p.b.n_tiles;
