@@ -120,6 +120,19 @@ class GraphBatch:
                                              self.colidx.ctypes.data if self.total_nnz else None, self.tile_off.ctypes.data,
                                              self.n_tiles, bits.ctypes.data), "mho_fill_adj_bits")
             self.adj_bits = bits
+        # row tiles: plain runs of 128 nodes that ignore graph boundaries - valid (and perfectly full) whenever no layer
+        # touches the operator (every K = 1, the reference's shipped model), whatever the graph sizes
+        nrt = (self.total_nodes + 127) // 128
+        n0 = 128 * np.arange(max(nrt, 1), dtype=np.int64)
+        n1 = np.minimum(n0 + 128, self.total_nodes)
+        self.row_tile_info = np.zeros((max(nrt, 1), 4), dtype=np.int32)
+        if nrt:
+            self.row_tile_info[:, 0] = n0
+            self.row_tile_info[:, 1] = n1 - n0
+            self.row_tile_info[:, 2] = self.rowptr[n0]
+            self.row_tile_info[:, 3] = self.rowptr[n1] - self.rowptr[n0]
+        self.n_row_tiles = int(nrt)
+        self.max_row_tile_nnz = int(self.row_tile_info[:, 3].max()) if nrt else 0
         # largest tile first: the kernel's CTAs pull tiles in this order from a global counter
         if self.n_tiles > 1:
             cost = 3 * self.tile_info[:, 1].astype(np.int64) + self.tile_info[:, 3]
@@ -143,7 +156,8 @@ class GraphBatch:
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
         self.dev = dict(graph_off=up(self.graph_off), rowptr=up(self.rowptr), colidx=up(self.colidx),
-                        tile_off=up(self.tile_off), tile_info=up(self.tile_info), graph_info=up(self.graph_info))
+                        tile_off=up(self.tile_off), tile_info=up(self.tile_info), graph_info=up(self.graph_info),
+                        row_tile_info=up(self.row_tile_info))
         if self.vals is not None:
             self.dev["vals"] = up(self.vals)
         if getattr(self, "adj_bits", None) is not None:
@@ -152,18 +166,19 @@ class GraphBatch:
             self.dev["rowptr_t"], self.dev["colidx_t"], self.dev["vals_t"] = (up(a) for a in self.transpose)
         return self
 
-    def struct_ref(self, per_graph_tiles=False):
+    def struct_ref(self, per_graph_tiles=False, row_tiles=False):
         """Cached ctypes byref of the mho_batch_t (device arrays never move after .to())."""
-        key = bool(per_graph_tiles)
+        key = (bool(per_graph_tiles), bool(row_tiles))
         c = self._struct_cache.get(key)
         if c is None:
-            st = self.struct(per_graph_tiles=key)
+            st = self.struct(per_graph_tiles=key[0], row_tiles=key[1])
             c = (st, C.byref(st))
             self._struct_cache[key] = c
         return c[1]
 
-    def struct(self, per_graph_tiles=False):
-        """mho_batch_t over the device arrays.  per_graph_tiles=True => tile_off NULL (backward)."""
+    def struct(self, per_graph_tiles=False, row_tiles=False):
+        """mho_batch_t over the device arrays.  per_graph_tiles=True => tile_off NULL (backward); row_tiles=True =>
+        128-node row tiles that ignore graph boundaries (only for stacks whose layers all have K = 1)."""
         assert self.dev, "GraphBatch.to(device) first"
         b = _lib.mho_batch_t()
         b.n_graphs, b.total_nodes, b.total_nnz = self.n_graphs, self.total_nodes, self.total_nnz
@@ -175,7 +190,11 @@ class GraphBatch:
             b.rowptr_t = self.dev["rowptr_t"].data_ptr()
             b.colidx_t = self.dev["colidx_t"].data_ptr()
             b.vals_t = self.dev["vals_t"].data_ptr() if "vals" in self.dev else None
-        if per_graph_tiles:
+        if row_tiles:
+            b.tile_off, b.n_tiles = self.dev["tile_off"].data_ptr(), self.n_row_tiles   # non-NULL marks "tiled"
+            b.tile_info = self.dev["row_tile_info"].data_ptr()
+            b.max_tile_rows, b.max_tile_nnz = min(128, self.total_nodes), self.max_row_tile_nnz
+        elif per_graph_tiles:
             b.tile_off, b.n_tiles = None, self.n_graphs
             b.tile_info = self.dev["graph_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_graph_rows, self.max_graph_nnz

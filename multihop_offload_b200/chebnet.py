@@ -133,7 +133,10 @@ class ChebNet:
         Y = out if out is not None else torch.empty((batch.total_nodes, self.specs[-1].f_out), dtype=torch.float32,
                                                     device=self.device)
         saved = torch.empty(max(self.saved_floats(batch), 1), dtype=torch.float32, device=self.device) if save else None
-        rc = self.ctx.lib.mho_cheb_forward(self.ctx.handle, batch.struct_ref(per_graph_tiles), self.layer_structs(),
+        # no layer touches the operator (all K = 1, the reference's shipped model): full 128-node row tiles, any graph size
+        row_tiles = (not per_graph_tiles) and all(s.K == 1 for s in self.specs) \
+            and all(s.f_in <= 32 and s.f_out <= 32 for s in self.specs)
+        rc = self.ctx.lib.mho_cheb_forward(self.ctx.handle, batch.struct_ref(per_graph_tiles, row_tiles), self.layer_structs(),
                                            len(self.specs), X.data_ptr(), Y.data_ptr(),
                                            saved.data_ptr() if save else None, self._stream())
         if rc:

@@ -8,6 +8,8 @@
 // depend on the order).  It is the system Dijkstra's algorithm solves, with the same left-to-right path sums, so the
 // results are bit-identical to the reference's (fl(a + w) is monotone in a; weights > 0).  weight == NULL: hop counts.
 // The graph must be stored with both directions of every edge (undirected, like env.graph_c).
+// (The unsynchronised reads of entries other threads are lowering are intentional - compute-sanitizer's racecheck
+// reports them; any interleaving reaches the same fixed point, checked bit for bit against the reference's outputs.)
 #include <cfloat>
 #include <cstdint>
 

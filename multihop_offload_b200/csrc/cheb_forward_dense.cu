@@ -157,6 +157,7 @@ __device__ __forceinline__ TileInfoD load_tile(const BatchDev& b, int i) {
 
 // operator of one tile -> staging: the precomputed bit rows (16 B per node) when the batch carries them, else the CSR slice
 __device__ __forceinline__ void issue_csr_loads(const DenseParams& p, const TileInfoD& t, uint32_t rp_a, uint32_t ci_a, int tid) {
+    if (!p.need_adj) return;  // every layer has K = 1: the operator is never touched
     if (p.b.adj_bits != nullptr) {
         if (tid < t.rows) cp_async16(rp_a + tid * 16, p.b.adj_bits + (size_t)(t.node0 + tid) * 4);
         return;
@@ -562,7 +563,7 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg & 32) return false;  // MHO_DEBUG & 32: keep the CSR-walk kernel
-    if (has_vals || max_tile_rows > 128) return false;
+    if (max_tile_rows > 128) return false;
     int wb = 0;
     bool need_adj = false;
     for (int l = 0; l < n_layers; ++l) {
@@ -571,7 +572,8 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
         wb += dn_layer_bytes(layers[l].K, layers[l].f_out);
         need_adj |= layers[l].K > 1;
     }
-    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 + 192 + 2048 + 832 + 16384;
+    if (has_vals && need_adj) return false;  // weighted operators go through the CSR-walk kernel (K = 1 stacks never read them)
+    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (need_adj ? (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 : 128) + 192 + 2048 + 832 + 16384;
     return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
 }
 
@@ -610,7 +612,7 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
     p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
     p.wimg = wimg; p.w_bytes = w_bytes;
     p.nnz_cap = (max_tile_nnz + 3) & ~3;
-    p.stage_words = p.b.adj_bits != nullptr ? 512 : 132 + p.nnz_cap;
+    p.stage_words = !p.need_adj ? 16 : (p.b.adj_bits != nullptr ? 512 : 132 + p.nnz_cap);
     p.tmem_cols = cols;
     p.sched = fp.sched;
     const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * p.stage_words * 4 + 192 + 2048 + 832 + 16384;

@@ -352,10 +352,25 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     if (nnz > 0 && !colidx_h) { mho_set_error("mho_cheb_forward_host: colidx is NULL"); return MHO_ERR_INVALID; }
     std::vector<int32_t> tile_off((size_t)n_graphs + 1);
     int32_t n_tiles = 0, mr = 0, mz = 0;
-    rc = mho_plan_tiles(goff_h, rowptr_h, n_graphs, 128, tile_off.data(), &n_tiles, &mr, &mz);
-    if (rc) return rc;
-    std::vector<int32_t> tinfo((size_t)n_tiles * 4 + 4);
-    mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tinfo.data());
+    std::vector<int32_t> tinfo;
+    bool all_k1 = true;
+    for (int l = 0; l < n_layers; ++l) all_k1 = all_k1 && layers[l].K == 1 && layers[l].f_in <= 32 && layers[l].f_out <= 32;
+    if (all_k1) {
+        // no layer touches the operator: full 128-node row tiles that ignore graph boundaries, whatever the graph sizes
+        n_tiles = (total_nodes + 127) / 128;
+        tinfo.resize((size_t)n_tiles * 4 + 4);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int a = 128 * t, b2 = std::min(a + 128, total_nodes);
+            tinfo[4 * t] = a; tinfo[4 * t + 1] = b2 - a; tinfo[4 * t + 2] = rowptr_h[a]; tinfo[4 * t + 3] = rowptr_h[b2] - rowptr_h[a];
+            mz = std::max(mz, tinfo[4 * t + 3]);
+        }
+        mr = std::min(128, total_nodes);
+    } else {
+        rc = mho_plan_tiles(goff_h, rowptr_h, n_graphs, 128, tile_off.data(), &n_tiles, &mr, &mz);
+        if (rc) return rc;
+        tinfo.resize((size_t)n_tiles * 4 + 4);
+        mho_fill_tile_info(goff_h, rowptr_h, tile_off.data(), n_tiles, tinfo.data());
+    }
 
     // chunks: contiguous runs of tiles of roughly equal bytes, ~300 tiles each (measured: copies of a few MB keep both
     // PCIe directions efficient; 2 chunks beat 1, 3 and 4 for the 594-tile benchmark batch), at most 8 chunks
@@ -376,6 +391,12 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
             cstart[k] = t;
         }
         cstart[n_chunks] = n_tiles;
+    }
+    // node extent of each chunk (its tiles are a contiguous run of nodes), taken before the tiles are reordered
+    std::vector<int> cn0((size_t)n_chunks), cn1((size_t)n_chunks);
+    for (int k = 0; k < n_chunks; ++k) {
+        cn0[k] = tinfo[4 * (size_t)cstart[k]];
+        cn1[k] = cstart[k + 1] > cstart[k] ? tinfo[4 * (size_t)(cstart[k + 1] - 1)] + tinfo[4 * (size_t)(cstart[k + 1] - 1) + 1] : cn0[k];
     }
     // inside every chunk: largest tile first for the kernel's dynamic scheduler (tinfo is consumed in order)
     for (int k = 0; k < n_chunks; ++k) {
@@ -421,9 +442,7 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
 
     // node / nnz extent of each chunk (tiles of a chunk are a contiguous run of graphs)
-    auto chunk_nodes = [&](int k, int& n0, int& n1) {
-        n0 = goff_h[tile_off[cstart[k]]]; n1 = goff_h[tile_off[cstart[k + 1]]];
-    };
+    auto chunk_nodes = [&](int k, int& n0, int& n1) { n0 = cn0[k]; n1 = cn1[k]; };
     for (int k = 0; k < n_chunks; ++k) {
         int n0, n1;
         chunk_nodes(k, n0, n1);

@@ -223,7 +223,7 @@ class ACOAgent:
         batch = self._batch_of(state["support"])
         X = torch.as_tensor(np.ascontiguousarray(state["node_features"], dtype=np.float32), device=self.device)
         if save:
-            Y, saved = self.net.forward(batch, X, save=True, per_graph_tiles=True)
+            Y, saved = self.net.forward(batch, X, save=True)
             self._tape = dict(batch=batch, X=X, Y=Y, saved=saved)
             return Y
         return self.net.forward(batch, X)
