@@ -38,7 +38,7 @@ struct BwdParams {
 };
 
 template <bool HAS_VALS, bool STAGED>
-__global__ void __launch_bounds__(MHO_THREADS, 1) cheb_backward_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(MHO_THREADS, 4) cheb_backward_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t tile_bytes = (size_t)p.rows_cap * 128;
@@ -223,20 +223,32 @@ __global__ void __launch_bounds__(MHO_THREADS, 1) cheb_backward_kernel(const __g
     }
 }
 
-// deterministic sum over graphs: out[p] = sum_g grads[g][p], fixed order, 4 independent chains
-__global__ void grads_sum_kernel(const float* __restrict__ grads, float* __restrict__ out, int n_graphs, long long n_params) {
+// deterministic sum over graphs, out[p] = sum_g grads[g][p], in two fixed-order stages so that enough loads are in
+// flight: slice s of MHO_SUM_SLICES sums its run of graphs (4 independent chains), then the slices are added in order.
+#define MHO_SUM_SLICES 32
+__global__ void grads_sum_stage1(const float* __restrict__ grads, float* __restrict__ part, int n_graphs, long long n_params) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_params) return;
+    const int per = (n_graphs + MHO_SUM_SLICES - 1) / MHO_SUM_SLICES;
+    const int g0 = blockIdx.y * per, g1 = min(g0 + per, n_graphs);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int g = 0;
-    for (; g + 4 <= n_graphs; g += 4) {
+    int g = g0;
+    for (; g + 4 <= g1; g += 4) {
         s0 += grads[(size_t)(g + 0) * n_params + p];
         s1 += grads[(size_t)(g + 1) * n_params + p];
         s2 += grads[(size_t)(g + 2) * n_params + p];
         s3 += grads[(size_t)(g + 3) * n_params + p];
     }
-    for (; g < n_graphs; ++g) s0 += grads[(size_t)g * n_params + p];
-    out[p] = (s0 + s1) + (s2 + s3);
+    for (; g < g1; ++g) s0 += grads[(size_t)g * n_params + p];
+    part[(size_t)blockIdx.y * n_params + p] = (s0 + s1) + (s2 + s3);
+}
+__global__ void grads_sum_stage2(const float* __restrict__ part, float* __restrict__ out, long long n_params) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_params) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < MHO_SUM_SLICES; ++i) s += part[(size_t)i * n_params + p];
+    out[p] = s;
 }
 
 static size_t bwd_smem_bytes(int rows_cap, int nnz_cap, int w_floats, bool has_vals) {
@@ -329,10 +341,14 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     c->launches += 1;
     if (grads_sum) {
         const int threads = 128;
-        grads_sum_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(grads_per_graph, grads_sum, b->n_graphs, P);
+        float* part = (float*)mho_scratch(c, 1, (size_t)MHO_SUM_SLICES * P * sizeof(float));
+        if (!part) { mho_set_error("mho_cheb_backward: cudaMalloc of the reduction scratch failed"); return MHO_ERR_CUDA; }
+        const dim3 g1((unsigned)((P + threads - 1) / threads), MHO_SUM_SLICES);
+        grads_sum_stage1<<<g1, threads, 0, st>>>(grads_per_graph, part, b->n_graphs, P);
+        grads_sum_stage2<<<g1.x, threads, 0, st>>>(part, grads_sum, P);
         e = cudaGetLastError();
         if (e != cudaSuccess) { mho_set_error("grads_sum launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
-        c->launches += 1;
+        c->launches += 2;
     }
     return MHO_OK;
 }
