@@ -349,6 +349,22 @@ def run_gpu_arm(args):
     e5b.record()
     barrier()
     stack5_ms = e5a.elapsed_time(e5b) / n5
+    # third series: forward (activations kept) + VJP to one flat gradient per graph + deterministic sum
+    dYt = torch.randn((n_nodes, w["F"]), device=dev)
+    def train_step():
+        Yt, saved = net.forward(batches[0], Xs[0], save=True)
+        net.backward(batches[0], Xs[0], Yt, saved, dYt)
+    for _ in range(3):
+        train_step()
+    barrier()
+    eta, etb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nt = max(5, min(args.steps, 30))
+    eta.record()
+    for _ in range(nt):
+        train_step()
+    etb.record()
+    barrier()
+    train_ms = eta.elapsed_time(etb) / nt
 
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -387,7 +403,9 @@ def run_gpu_arm(args):
                          "tflops_algorithmic": algorithmic_flops(w) / (per_launch_ms * 1e-3) / 1e12},
         }
         out["series"] = {"reference_stack_4_32_32_32_32_1_K1": {
-            "value": args.graphs / (stack5_ms * 1e-3), "unit": "graph forwards/s per GPU (5 fused layers, rank 0)", "ms_per_step": stack5_ms}}
+            "value": args.graphs / (stack5_ms * 1e-3), "unit": "graph forwards/s per GPU (5 fused layers, rank 0)", "ms_per_step": stack5_ms},
+            "forward_backward_K5_32_32": {
+            "value": args.graphs / (train_ms * 1e-3), "unit": "graph forward+VJP steps/s per GPU (per-graph gradients + their sum, rank 0)", "ms_per_step": train_ms}}
         if world == 1 and not args.no_cpu:
             v, cores, passes, dt = cpu_reference_rate(w, seconds=args.cpu_seconds, threads=1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
