@@ -123,7 +123,12 @@ int mho_fill_adj_bits(const int32_t* graph_off_host, const int32_t* rowptr_host,
 /* ---- forward: replaces ACOAgent.predict -> self.model([x_in, a_in])
  * (gnn_offloading_agent.py:144-150) for a whole batch.  X [total_nodes, layers[0].f_in],
  * Y [total_nodes, layers[n-1].f_out], both row-major fp32.  `saved` (nullable) receives the
- * inputs of layers 1..n-1 (the hidden activations) for the VJP: mho_saved_bytes() bytes. */
+ * inputs of layers 1..n-1 (the hidden activations) for the VJP: mho_saved_bytes() bytes.
+ * Kernel selection (results agree to fp32 round-off): with tile_off + tile_info, tiles of <= 128 nodes, <= 32
+ * features per layer, K <= 5 and either a binary operator (vals == NULL) or K = 1 everywhere, the all-tensor-core
+ * kernel runs (tcgen05 / TMEM, csrc/cheb_forward_dense.cu); otherwise the CSR-walk kernel (csrc/cheb_forward.cu).
+ * With K = 1 in every layer the operator is never read and tile_info may describe ANY runs of <= 128 consecutive nodes
+ * (they need not respect graph boundaries).  With vals == NULL the CSR must not hold duplicate entries. */
 int mho_cheb_forward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
                      int32_t n_layers, const float* X, float* Y, void* saved, mho_stream_t stream);
 size_t mho_saved_bytes(const mho_batch_t* batch, const mho_layer_t* layers, int32_t n_layers);
