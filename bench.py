@@ -50,6 +50,28 @@ def ba_csr(n, seed):
     return indptr, (np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64))
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that cudaHostAlloc'd staging buffers
+    are local to the GPU's PCIe root (one rank per GPU: 8 ranks otherwise crowd the first socket).  Best effort."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def make_workload(n_graphs, rank=0, fixed_n=None, K=5, F=32, pack=True):
     rng = np.random.default_rng(0 + 7919 * rank)
     sizes = np.full(n_graphs, fixed_n) if fixed_n else rng.choice(SIZES, size=n_graphs)
@@ -204,7 +226,7 @@ def workload_config(args, w):
             "graphs_per_gpu": args.graphs, "nodes_per_gpu": int(w["graph_off"][-1]), "nnz_per_gpu": int(w["rowptr"][-1]),
             "parallelism": "graph-instance sharding, no data-path collective",
             "l2": "rotating over distinct input/output sets > 2x L2",
-            "streams": "%d CUDA streams, one library context each; consecutive steps are independent batches and may overlap at their boundaries" % int(getattr(args, "streams", 1)),
+            "numa_node": getattr(args, "numa_node", None), "streams": "%d CUDA streams, one library context each; consecutive steps are independent batches and may overlap at their boundaries" % int(getattr(args, "streams", 1)),
             "batch_order": "graphs laid out in tile-packing order (first-fit decreasing, multihop_offload_b200.pack_order)"}
 
 
@@ -225,6 +247,7 @@ def run_gpu_arm(args):
                          "(use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    args.numa_node = bind_to_gpu_numa_node(torch, local)   # page-locked staging buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
