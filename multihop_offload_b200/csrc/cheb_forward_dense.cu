@@ -22,6 +22,7 @@
 // per 16 nodes covers the three parts).  Shared memory per CTA (2 CTAs / SM, tensor memory is the limit): part tiles
 // 24 KB, the bf16 weight parts of every layer, two operator staging sets, a 16 KB input staging tile.
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -52,7 +53,10 @@ struct DenseParams {
     float* saved;
     const unsigned char* wimg;         // per layer: [part h][part m][part l] (n_rows x 64 B each) + 128 B bias row
     int w_off[MHO_MAX_LAYERS];         // byte offset of each layer's block (multiples of 1024)
-    int w_bytes;
+    int w_bytes;                       // bytes of the shared-memory weight region
+    int w_resident;                    // 1: every layer's images stay in shared memory; 0: two slots of w_slot bytes, layers stream through
+    int w_slot;
+    int w_lbytes[MHO_MAX_LAYERS];      // bytes of each layer's block
     int nnz_cap;                       // staged colidx capacity (multiple of 4)
     int stage_words;                   // words per operator staging set: 512 (bit rows) or 132 + nnz_cap (CSR slice)
     int need_adj;                      // some layer has K > 1
@@ -273,7 +277,11 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
 
     // from here on global memory written by earlier launches in the stream is read
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int c = tid; c < p.w_bytes / 16; c += DN_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
+    {   // resident: every layer's images; streaming: the first layer's into slot 0
+        const int nb = p.w_resident ? p.w_bytes : p.w_lbytes[0];
+        for (int c = tid; c < nb / 16; c += DN_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
+    }
+    int wslot = 0;  // streaming mode: the slot holding the current layer's images
 
     // ---- tile scheduler (dynamic from the third tile of a CTA on; the last CTA out re-arms the counters)
     // the first two tiles of every CTA are static (no round trip to the counter before work starts); the counter
@@ -330,8 +338,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
             const int K = L.K;
             const int nblk = dn_nblk(K, L.f_out);
             const int n_rows = K * nblk;
-            const uint32_t w_l = w_a + (uint32_t)p.w_off[li];
-            const float* bias_s = reinterpret_cast<const float*>(w_s + p.w_off[li] + (size_t)n_rows * 192);
+            const int w_pos = p.w_resident ? p.w_off[li] : wslot * p.w_slot;
+            const uint32_t w_l = w_a + (uint32_t)w_pos;
+            const float* bias_s = reinterpret_cast<const float*>(w_s + w_pos + (size_t)n_rows * 192);
+            if (!p.w_resident) cp_async_wait<0>();  // this layer's images (issued one layer ago) have landed
 
             PROBE(4);
             // ---- P = X_l [W_0 | ... | W_K-1]: six part products, two 16-wide K steps each
@@ -403,6 +413,18 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
                     PROBE(32);
                     tmem_st_32x32b_x16(tmem_row + adj_col + (uint32_t)(cb * 16), aw);
                 }
+            if (!p.w_resident) {
+                // the next layer's images (the first layer's, for the next tile, after the last) go to the other slot: its
+                // last readers were the previous layer's UMMAs and epilogue, complete before this layer's barrier
+                const int ln = (li + 1 == p.n_layers) ? 0 : li + 1;
+                if (ln != 0 || has_nxt) {
+                    const uint32_t dst = w_a + (uint32_t)((wslot ^ 1) * p.w_slot);
+                    const unsigned char* src = p.wimg + p.w_off[ln];
+                    for (int c = tid; c < p.w_lbytes[ln] / 16; c += DN_THREADS) cp_async16(dst + (uint32_t)c * 16u, src + (size_t)c * 16);
+                }
+                cp_async_commit();
+                wslot ^= 1;
+            }
             // the next tile's operator slice and input rows stream in behind the first layer's UMMAs (every thread
             // has read the input staging tile: the barrier above)
             if (li == 0) {
@@ -573,8 +595,12 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
         need_adj |= layers[l].K > 1;
     }
     if (has_vals && need_adj) return false;  // weighted operators go through the CSR-walk kernel (K = 1 stacks never read them)
-    const size_t smem = (size_t)3 * DN_PART_BYTES + wb + (need_adj ? (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 : 128) + 192 + 2048 + 832 + 16384;
-    return smem + 1024 <= (size_t)(228 * 1024) / 2 && smem <= (size_t)max_smem_optin;
+    int wmax = 0;
+    for (int l = 0; l < n_layers; ++l) wmax = std::max(wmax, dn_layer_bytes(layers[l].K, layers[l].f_out));
+    const size_t rest = (size_t)3 * DN_PART_BYTES + (need_adj ? (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 : 128) + 192 + 2048 + 832 + 16384;
+    const size_t budget = std::min((size_t)(228 * 1024) / 2 - 1024, (size_t)max_smem_optin);
+    // all layers' weight images resident, or (multi-layer stacks with K > 1) two slots the layers stream through
+    return rest + wb <= budget || (n_layers > 1 && rest + 2 * (size_t)wmax <= budget);
 }
 
 int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off) {
@@ -610,12 +636,21 @@ cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, co
         while (cols < n) cols <<= 1;
     }
     p.X = fp.X; p.Y = fp.Y; p.saved = fp.saved;
-    p.wimg = wimg; p.w_bytes = w_bytes;
+    p.wimg = wimg;
+    int wmax = 0;
+    for (int l = 0; l < fp.n_layers; ++l) {
+        p.w_lbytes[l] = (l + 1 < fp.n_layers ? w_off[l + 1] : w_bytes) - w_off[l];
+        wmax = std::max(wmax, p.w_lbytes[l]);
+    }
     p.nnz_cap = (max_tile_nnz + 3) & ~3;
     p.stage_words = !p.need_adj ? 16 : (p.b.adj_bits != nullptr ? 512 : 132 + p.nnz_cap);
     p.tmem_cols = cols;
     p.sched = fp.sched;
-    const size_t smem = (size_t)3 * DN_PART_BYTES + w_bytes + (size_t)2 * p.stage_words * 4 + 192 + 2048 + 832 + 16384;
+    const size_t rest = (size_t)3 * DN_PART_BYTES + (size_t)2 * p.stage_words * 4 + 192 + 2048 + 832 + 16384;
+    p.w_resident = (fp.n_layers == 1 || rest + (size_t)w_bytes <= (size_t)(228 * 1024) / 2 - 1024) ? 1 : 0;
+    p.w_slot = wmax;
+    p.w_bytes = p.w_resident ? w_bytes : 2 * wmax;
+    const size_t smem = rest + (size_t)p.w_bytes;
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);

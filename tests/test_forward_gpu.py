@@ -312,3 +312,34 @@ def test_two_streams_two_contexts_equal_single_stream(torch_cuda, golden_dir):
     torch_cuda.cuda.synchronize()
     for i in range(len(Xs)):
         assert torch_cuda.equal(outs[i], want[i]), i
+
+
+def test_dense_kernel_streams_weights_of_deep_k_stacks(torch_cuda):
+    """Five-layer stacks with K = 3 / K = 4: the bf16 weight images of all layers do not fit next to the tiles, so the
+    tensor-core kernel streams them layer by layer through two shared-memory slots (many tiles per CTA: the slots are
+    recycled across tiles); hidden activations are saved for the VJP."""
+    from multihop_offload_b200 import GraphBatch, reference_stack
+    rng = np.random.default_rng(91)
+    sizes = rng.choice(np.arange(20, 111, 10), size=700)
+    mats = O.make_batch(sizes, seed0=12000)
+    n = int(sizes.sum())
+    batch = GraphBatch.from_scipy(mats, tile_rows=128, device="cuda:0")
+    assert batch.n_tiles > 2 * 296 // 2   # several tiles per CTA
+    for K in (3, 4):
+        specs = reference_stack(K=K)
+        ws = random_weights(specs, rng, 0.15)
+        net = _net(specs, ws)
+        X = rng.normal(size=(n, 4))
+        Y, saved = net.forward(batch, torch_cuda.from_numpy(X.astype(np.float32)).cuda(), save=True)
+        acts = [s.act for s in specs]
+        ref, zscale = oracle_batch_forward(mats, X, ws, acts, 0.2, return_scale=True)
+        err = rel_err(Y.cpu().numpy(), ref, batch.graph_off, zscale)
+        # five raw-adjacency layers of order K amplify round-off (values grow by (2 rho)^K per layer): the yardstick is
+        # what plain fp32 arithmetic (numpy) loses on the same stack
+        err32 = rel_err(numpy_fp32_forward(mats, X, ws, acts, 0.2), ref, batch.graph_off, zscale)
+        print("K", K, "err", err, "numpy-fp32 err", err32)
+        assert err < max(TOL, 3 * err32), (K, err, err32)
+        h3 = oracle_batch_forward(mats, X, ws[:3], acts[:3], 0.2)
+        off = n * (32 + 32)
+        got = saved[off: off + n * 32].view(n, 32).cpu().numpy()
+        assert rel_err(got, h3, batch.graph_off) < TOL, K
