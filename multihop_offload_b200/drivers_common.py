@@ -80,8 +80,15 @@ def run_method(method, env, agent, apsp, explore=0.0):
         for link, delay in zip(env.link_list, dlist_bl):
             src, dst = link
             env.graph_c[src][dst]["delay"] = delay if delay > 0 else float(env.T)
-        sp_baseline = apsp(env.graph_c, weight="delay")
-        sp_hop = apsp(env.graph_c, weight=None)
+        if getattr(agent, "_on_gpu", lambda: False)():
+            # same shortest-path matrices from mho_apsp (bit-identical to the reference's Dijkstra)
+            M = np.zeros((env.num_nodes, env.num_nodes))
+            for (src, dst) in env.graph_c.edges:
+                M[src, dst] = M[dst, src] = env.graph_c[src][dst]["delay"]
+            sp_baseline, sp_hop = agent._shortest_paths(env, M, apsp)
+        else:
+            sp_baseline = apsp(env.graph_c, weight="delay")
+            sp_hop = apsp(env.graph_c, weight=None)
         np.fill_diagonal(sp_baseline, dproc_bl)
         env.offloading(sp_baseline, sp_hop)
         delay_links, delay_nodes, _ = env.run()
