@@ -250,12 +250,12 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
     int* csr0 = reinterpret_cast<int*>(w_s + p.w_bytes);
     const int rp_words = (128 + 2 + 3) & ~3;
     const int csr_words = p.stage_words;
-    int* s_idx = csr0 + 2 * csr_words;   // [0..1] first two tile indices, [2..3] mbarrier, [4] TMEM base, [8..12] next tile {index, info}
+    int* s_idx = csr0 + 2 * csr_words;   // [2..3] mbarrier, [4] TMEM base, [8] index and [12..15] bounds of the tile after next
     const uint32_t parts_a = smem_u32(parts_s), w_a = smem_u32(w_s), csr_a0 = smem_u32(csr0);
     const uint32_t mbar = smem_u32(s_idx + 2), tslot = smem_u32(s_idx + 4);
     uint2* lut_s = reinterpret_cast<uint2*>(s_idx + 16);                  // 4 adjacency bits -> two bf16 pairs
     unsigned int* mask_s = reinterpret_cast<unsigned int*>(s_idx + 48);   // [128 rows][4] adjacency bits of the tile
-    const uint32_t xs_a = smem_u32(s_idx + 48 + 512 + 208);               // 16 KB input staging (1024 B aligned: see the host side)
+    const uint32_t xs_a = smem_u32(s_idx + 48 + 512 + 208);               // 16 KB input staging tile
     const bool x_staged = (p.layers[0].f_in & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0;  // 16 B cp.async chunks
     if (tid < 16)
         lut_s[tid] = make_uint2(((tid & 1) ? 0x3F80u : 0u) | ((tid & 2) ? 0x3F800000u : 0u), ((tid & 4) ? 0x3F80u : 0u) | ((tid & 8) ? 0x3F800000u : 0u));
