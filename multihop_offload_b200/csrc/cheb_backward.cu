@@ -331,7 +331,7 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     p.nnz_cap = nnz_cap;
     int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > 4) per_sm = 4;   // 56-64 registers x 256 threads: four CTAs fit the register file
     int grid = c->num_sms * per_sm;
     if (grid > b->n_graphs) grid = b->n_graphs;
     cudaError_t e;
