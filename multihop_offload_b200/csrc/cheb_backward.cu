@@ -100,28 +100,60 @@ __global__ void __launch_bounds__(MHO_THREADS, 4) cheb_backward_kernel(const __g
             __syncthreads();
 
             // =========================== phase A: db, dW_k ===========================
-            // thread (warp, lane): output column o = lane, input features f = 4*warp .. 4*warp+3
+            // dW_k = T_k^T G as register-blocked rank-1 updates: the rows are dealt to four groups of two warps; inside a
+            // group thread j owns the 4 x 4 block (f = 4 (j >> 3).., o = 4 (j & 7)..): two LDS.128 feed 16 FMAs per row.
+            // The four partial blocks meet in shared memory (the W^T region, idle until phase B) and are added in a fixed
+            // order, one float4 of the result per thread.
+            const int rg = warp >> 1, jj = ((warp & 1) << 5) | lane;
+            const uint32_t fblk = (uint32_t)(jj >> 3), oblk = (uint32_t)(jj & 7);
+            float* red_s = Wt_s;                       // [4 groups][32 f][32 o]
+            float* redb_s = Wt_s + 4 * 1024;           // [4 groups][32 o]
             int cur = 0;
             for (int k = 0; k < K; ++k) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, bsum = 0.f;
+                float acc[4][4], bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
                 const uint32_t Tk = R_a[cur];
-                for (int i = 0; i < rows; ++i) {
-                    const float gv = lds_f32(G_a + (swz_row((uint32_t)i) ^ key));
-                    const uint4 t = lds_u128(Tk + ((uint32_t)i << 7) + ((((uint32_t)warp) ^ ((uint32_t)i & 7u)) << 4));
-                    a0 = fmaf(__uint_as_float(t.x), gv, a0);
-                    a1 = fmaf(__uint_as_float(t.y), gv, a1);
-                    a2 = fmaf(__uint_as_float(t.z), gv, a2);
-                    a3 = fmaf(__uint_as_float(t.w), gv, a3);
-                    bsum += gv;
+                for (int i = rg; i < rows; i += 4) {
+                    const uint32_t rowa = (uint32_t)i << 7, sw = (uint32_t)i & 7u;
+                    const uint4 tq = lds_u128(Tk + rowa + ((fblk ^ sw) << 4));
+                    const uint4 gq = lds_u128(G_a + rowa + ((oblk ^ sw) << 4));
+                    const float t[4] = {__uint_as_float(tq.x), __uint_as_float(tq.y), __uint_as_float(tq.z), __uint_as_float(tq.w)};
+                    const float gg[4] = {__uint_as_float(gq.x), __uint_as_float(gq.y), __uint_as_float(gq.z), __uint_as_float(gq.w)};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(t[a], gg[b], acc[a][b]);
+                    if (k == 0 && fblk == 0u) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) bs[b] += gg[b];
+                    }
                 }
-                if (lane < fo) {
-                    float* dst = gout + L.param_off + (size_t)k * fi * fo + lane;
-                    const int f0 = warp * 4;
-                    if (f0 + 0 < fi) dst[(size_t)(f0 + 0) * fo] = a0;
-                    if (f0 + 1 < fi) dst[(size_t)(f0 + 1) * fo] = a1;
-                    if (f0 + 2 < fi) dst[(size_t)(f0 + 2) * fo] = a2;
-                    if (f0 + 3 < fi) dst[(size_t)(f0 + 3) * fo] = a3;
-                    if (k == 0 && warp == 0) gout[L.param_off + (size_t)K * fi * fo + lane] = bsum;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    *reinterpret_cast<float4*>(red_s + rg * 1024 + (int)(fblk * 4 + a) * 32 + (int)oblk * 4) =
+                        make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                if (k == 0 && fblk == 0u) *reinterpret_cast<float4*>(redb_s + rg * 32 + (int)oblk * 4) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+                __syncthreads();
+                {
+                    const int f = tid >> 3, o4 = (tid & 7) * 4;
+                    const float4 p0 = *reinterpret_cast<const float4*>(red_s + f * 32 + o4);
+                    const float4 p1 = *reinterpret_cast<const float4*>(red_s + 1024 + f * 32 + o4);
+                    const float4 p2 = *reinterpret_cast<const float4*>(red_s + 2048 + f * 32 + o4);
+                    const float4 p3 = *reinterpret_cast<const float4*>(red_s + 3072 + f * 32 + o4);
+                    const float v[4] = {((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y,
+                                        ((p0.z + p1.z) + p2.z) + p3.z, ((p0.w + p1.w) + p2.w) + p3.w};
+                    if (f < fi) {
+                        float* dst = gout + L.param_off + ((size_t)k * fi + f) * fo + o4;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (o4 + b < fo) dst[b] = v[b];
+                    }
+                    if (k == 0 && tid < 32 && tid < fo)
+                        gout[L.param_off + (size_t)K * fi * fo + tid] =
+                            ((redb_s[tid] + redb_s[32 + tid]) + redb_s[64 + tid]) + redb_s[96 + tid];
                 }
                 // T_{k+1} (forward operator A), in place over T_{k-1}
                 if (k + 1 < K) {
@@ -313,6 +345,7 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     if (p.rows_cap > MHO_MAX_TILE_ROWS) { mho_set_error("mho_cheb_backward: graph of %d nodes exceeds %d", b->max_tile_rows, MHO_MAX_TILE_ROWS); return MHO_ERR_TOO_LARGE; }
     int wf = 0;
     for (int l = 0; l < n_layers; ++l) { int v = layers[l].K * layers[l].f_out * 32; wf = v > wf ? v : wf; }
+    if (wf < 4 * 1024 + 128) wf = 4 * 1024 + 128;   // also the phase-A reduction scratch: 4 partial 32 x 32 blocks + 4 bias rows
     p.w_floats_cap = wf;
     const bool has_vals = b->vals != nullptr;
     if (has_vals && b->rowptr_t && !b->vals_t) { mho_set_error("mho_cheb_backward: vals_t missing for a weighted non-symmetric operator"); return MHO_ERR_INVALID; }
