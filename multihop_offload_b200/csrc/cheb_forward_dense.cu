@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) cheb_dense_kernel(const __grid_
 // -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
-bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, int max_tile_rows, int max_tile_nnz,
+bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, int max_tile_rows, int max_tile_nnz,
                          int max_smem_optin) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -597,7 +597,8 @@ bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals,
     if (has_vals && need_adj) return false;  // weighted operators go through the CSR-walk kernel (K = 1 stacks never read them)
     int wmax = 0;
     for (int l = 0; l < n_layers; ++l) wmax = std::max(wmax, dn_layer_bytes(layers[l].K, layers[l].f_out));
-    const size_t rest = (size_t)3 * DN_PART_BYTES + (need_adj ? (size_t)2 * (132 + ((max_tile_nnz + 3) & ~3)) * 4 : 128) + 192 + 2048 + 832 + 16384;
+    const size_t stage = !need_adj ? 16 : (has_bits ? 512 : (size_t)132 + ((max_tile_nnz + 3) & ~3));   // words per operator staging set
+    const size_t rest = (size_t)3 * DN_PART_BYTES + 2 * stage * 4 + 192 + 2048 + 832 + 16384;
     const size_t budget = std::min((size_t)(228 * 1024) / 2 - 1024, (size_t)max_smem_optin);
     // all layers' weight images resident, or (multi-layer stacks with K > 1) two slots the layers stream through
     return rest + wb <= budget || (n_layers > 1 && rest + 2 * (size_t)wmax <= budget);

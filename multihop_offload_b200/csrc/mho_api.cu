@@ -302,7 +302,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.sched = c->sched;
     // preferred: dense-adjacency tcgen05 path (binary adjacency, tiles <= 128 nodes, <= 32 features per layer)
     if (b->tile_off && b->tile_info && c->sched &&
-        cheb_dense_eligible(layers, n_layers, b->vals != nullptr, b->max_tile_rows, b->max_tile_nnz, c->max_smem_optin)) {
+        cheb_dense_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, b->max_tile_rows, b->max_tile_nnz, c->max_smem_optin)) {
         rc = ensure_prepared_dense(c, layers, n_layers, p.layers, (cudaStream_t)stream);
         if (rc) return rc;
         cudaError_t e = cheb_dense_launch(p, c->wdense, c->wd_off, c->wd_bytes, b->max_tile_nnz, c->num_sms, (cudaStream_t)stream);

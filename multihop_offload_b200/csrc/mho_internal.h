@@ -55,7 +55,7 @@ void mho_fill_layers(const mho_layer_t* layers, int n_layers, int total_nodes, L
 int wprep_layer_rows(int K, int f_out);
 cudaError_t prepare_weights_launch(const LayerDev* layers, int n_layers, const int* row_off, unsigned char* out,
                                    cudaStream_t st);
-bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, int max_tile_rows, int max_tile_nnz,
+bool cheb_dense_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, int max_tile_rows, int max_tile_nnz,
                          int max_smem_optin);
 int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off);
 cudaError_t prepare_dense_weights_launch(const LayerDev* layers, int n_layers, const int* w_off, unsigned char* out, cudaStream_t st);
