@@ -64,6 +64,7 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     for (auto& s : c->scratch) if (s.ptr) cudaFree(s.ptr);
     if (c->wprep) cudaFree(c->wprep);
     if (c->wdense) cudaFree(c->wdense);
+    if (c->wf16) cudaFree(c->wf16);
     if (c->sched) cudaFree(c->sched);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
@@ -99,7 +100,7 @@ extern "C" int mho_host_free(void* ptr) {
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
 
 extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
-    if (c) { c->wprep_valid = false; c->wdense_valid = false; }
+    if (c) { c->wprep_valid = false; c->wdense_valid = false; c->wf16_valid = false; }
     return MHO_OK;
 }
 
@@ -140,6 +141,7 @@ static int ensure_prepared_dense(mho_ctx* c, const mho_layer_t* layers, int n_la
     const size_t bytes = (size_t)c->wd_bytes;
     if (bytes > c->wdense_bytes) {
         if (c->wdense) cudaFree(c->wdense);
+    if (c->wf16) cudaFree(c->wf16);
         c->wdense = nullptr; c->wdense_bytes = 0;
         if (cudaMalloc((void**)&c->wdense, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
         c->wdense_bytes = bytes;
@@ -151,6 +153,25 @@ static int ensure_prepared_dense(mho_ctx* c, const mho_layer_t* layers, int n_la
     c->wdkey.clear();
     for (int l = 0; l < n_layers; ++l) c->wdkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
     c->wdense_valid = true;
+    return MHO_OK;
+}
+
+static int ensure_prepared_f16(mho_ctx* c, const mho_layer_t& L, const LayerDev& ld, cudaStream_t st) {
+    const mho_wkey k{L.W, L.b, L.K, L.f_in, L.f_out};
+    if (c->wf16_valid && k == c->wfkey) return MHO_OK;
+    const size_t bytes = (size_t)cheb_f16_weight_bytes(L.K);
+    if (bytes > c->wf16_bytes) {
+        if (c->wf16) cudaFree(c->wf16);
+        c->wf16 = nullptr; c->wf16_bytes = 0;
+        if (cudaMalloc((void**)&c->wf16, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
+        c->wf16_bytes = bytes;
+    }
+    if (cudaMemsetAsync(c->wf16, 0, bytes, st) != cudaSuccess) { mho_set_error("cudaMemsetAsync for prepared weights failed"); return MHO_ERR_CUDA; }
+    cudaError_t e = prepare_f16_weights_launch(ld, c->wf16, st);
+    if (e != cudaSuccess) { mho_set_error("prepare_f16_weights launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    c->wfkey = k;
+    c->wf16_valid = true;
     return MHO_OK;
 }
 
@@ -300,7 +321,18 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);
     p.X = X; p.Y = Y; p.saved = (float*)saved; p.total_nodes = b->total_nodes;
     p.sched = c->sched;
-    // preferred: dense-adjacency tcgen05 path (binary adjacency, tiles <= 128 nodes, <= 32 features per layer)
+    // one 32 -> 32 layer with 2 <= K <= 10 on a binary operator (the benchmark layer): second-generation tensor-core kernel
+    if (b->tile_off && b->tile_info &&
+        cheb_f16_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, saved != nullptr, b->max_tile_rows, b->max_tile_nnz, X, Y,
+                          b->adj_bits, c->max_smem_optin)) {
+        rc = ensure_prepared_f16(c, layers[0], p.layers[0], (cudaStream_t)stream);
+        if (rc) return rc;
+        cudaError_t e = cheb_f16_launch(p, c->wf16, b->max_tile_nnz, c->num_sms, (cudaStream_t)stream);
+        if (e != cudaSuccess) { mho_set_error("cheb_f16 launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+        c->launches += 1;
+        return MHO_OK;
+    }
+    // dense-adjacency tcgen05 path (binary adjacency, tiles <= 128 nodes, <= 32 features per layer, stacks)
     if (b->tile_off && b->tile_info && c->sched &&
         cheb_dense_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, b->max_tile_rows, b->max_tile_nnz, c->max_smem_optin)) {
         rc = ensure_prepared_dense(c, layers, n_layers, p.layers, (cudaStream_t)stream);

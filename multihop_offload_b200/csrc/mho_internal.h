@@ -38,6 +38,11 @@ struct mho_ctx {
     size_t wdense_bytes = 0;
     int wd_off[MHO_MAX_LAYERS] = {0};
     int wd_bytes = 0;
+    // fp16 two-part weight image of the second-generation dense kernel (cheb_forward_f16.cu), cached the same way
+    mho_wkey wfkey = {nullptr, nullptr, 0, 0, 0};
+    bool wf16_valid = false;
+    unsigned char* wf16 = nullptr;
+    size_t wf16_bytes = 0;
     int* sched = nullptr;  // two zero-initialised ints: dynamic tile scheduler state (self re-arming)
     int device = 0;
     int num_sms = 0;
@@ -61,6 +66,11 @@ int cheb_dense_weight_bytes(const mho_layer_t* layers, int n_layers, int* w_off)
 cudaError_t prepare_dense_weights_launch(const LayerDev* layers, int n_layers, const int* w_off, unsigned char* out, cudaStream_t st);
 cudaError_t cheb_dense_launch(const FwdParams& fp, const unsigned char* wimg, const int* w_off, int w_bytes, int max_tile_nnz,
                               int num_sms, cudaStream_t st);
+bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, bool has_saved, int max_tile_rows,
+                       int max_tile_nnz, const void* X, const void* Y, const void* bits, int max_smem_optin);
+int cheb_f16_weight_bytes(int K);
+cudaError_t prepare_f16_weights_launch(const LayerDev& L, unsigned char* out, cudaStream_t st);
+cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int max_tile_nnz, int num_sms, cudaStream_t st);
 cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
                         const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
