@@ -32,14 +32,16 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    extra = ["-DMHO_PROBE"] if os.environ.get("MHO_PROBE") else []
-    cmd = [nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + srcs + ["-lcudart"]
+    probe = bool(os.environ.get("MHO_PROBE"))   # instrumented build (clock marks printed by the forward kernels): libmho_probe.so
+    extra = ["-DMHO_PROBE"] if probe else []
+    out = LIB.replace("libmho.so", "libmho_probe.so") if probe else LIB
+    cmd = [nvcc()] + NVCC_FLAGS + extra + ["-o", out] + srcs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libmho.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

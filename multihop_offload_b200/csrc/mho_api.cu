@@ -26,6 +26,15 @@ void mho_set_error(const char* fmt, ...) {
         }                                                                                   \
     } while (0)
 
+// MHO_DEBUG & 128: report a pending (non-sticky) CUDA error at API boundaries - a call whose error return was dropped
+static void dbg_check(const char* where) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (!(dbg & 128)) return;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { fprintf(stderr, "[mho] pending CUDA error at %s: %s\n", where, cudaGetErrorString(e)); cudaGetLastError(); }
+}
+
 extern "C" const char* mho_last_error(void) { return g_err; }
 extern "C" int mho_version(void) { return MHO_VERSION; }
 
@@ -140,8 +149,7 @@ static int ensure_prepared_dense(mho_ctx* c, const mho_layer_t* layers, int n_la
     c->wd_bytes = cheb_dense_weight_bytes(layers, n_layers, c->wd_off);
     const size_t bytes = (size_t)c->wd_bytes;
     if (bytes > c->wdense_bytes) {
-        if (c->wdense) cudaFree(c->wdense);
-    if (c->wf16) cudaFree(c->wf16);
+        if (c->wdense) CUDA_TRY(cudaFree(c->wdense));
         c->wdense = nullptr; c->wdense_bytes = 0;
         if (cudaMalloc((void**)&c->wdense, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
         c->wdense_bytes = bytes;
@@ -303,6 +311,7 @@ extern "C" size_t mho_saved_bytes(const mho_batch_t* b, const mho_layer_t* layer
 extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_layer_t* layers, int32_t n_layers,
                                 const float* X, float* Y, void* saved, mho_stream_t stream) {
     if (!c) { mho_set_error("mho_cheb_forward: ctx is NULL"); return MHO_ERR_INVALID; }
+    dbg_check("mho_cheb_forward entry");
     int rc = validate_batch(b, "mho_cheb_forward");
     if (rc) return rc;
     rc = validate_layers(layers, n_layers, "mho_cheb_forward");
@@ -327,7 +336,9 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
                           b->adj_bits, c->max_smem_optin)) {
         rc = ensure_prepared_f16(c, layers[0], p.layers[0], (cudaStream_t)stream);
         if (rc) return rc;
-        cudaError_t e = cheb_f16_launch(p, c->wf16, b->max_tile_nnz, c->num_sms, (cudaStream_t)stream);
+        dbg_check("f16 prepared");
+        cudaError_t e = cheb_f16_launch(p, c->wf16, b->max_tile_nnz, c->num_sms, c->max_smem_optin, (cudaStream_t)stream);
+        dbg_check("f16 launched");
         if (e != cudaSuccess) { mho_set_error("cheb_f16 launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
         c->launches += 1;
         return MHO_OK;
@@ -338,6 +349,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
         rc = ensure_prepared_dense(c, layers, n_layers, p.layers, (cudaStream_t)stream);
         if (rc) return rc;
         cudaError_t e = cheb_dense_launch(p, c->wdense, c->wd_off, c->wd_bytes, b->max_tile_nnz, c->num_sms, (cudaStream_t)stream);
+        dbg_check("dense launched");
         if (e != cudaSuccess) { mho_set_error("cheb_dense launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
         c->launches += 1;
         return MHO_OK;

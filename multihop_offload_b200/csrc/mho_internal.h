@@ -70,7 +70,7 @@ bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, b
                        int max_tile_nnz, const void* X, const void* Y, const void* bits, int max_smem_optin);
 int cheb_f16_weight_bytes(int K);
 cudaError_t prepare_f16_weights_launch(const LayerDev& L, unsigned char* out, cudaStream_t st);
-cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int max_tile_nnz, int num_sms, cudaStream_t st);
+cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int max_tile_nnz, int num_sms, int max_smem_optin, cudaStream_t st);
 cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
                         const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
