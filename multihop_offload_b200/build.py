@@ -35,6 +35,9 @@ def build(force=False, verbose=False):
     probe = bool(os.environ.get("MHO_PROBE"))   # instrumented build (clock marks printed by the forward kernels): libmho_probe.so
     extra = ["-DMHO_PROBE"] if probe else []
     out = LIB.replace("libmho.so", "libmho_probe.so") if probe else LIB
+    if os.environ.get("MHO_EXTRA_FLAGS"):   # experiment builds: MHO_EXTRA_FLAGS="-DFOO" MHO_OUT=libmho_foo.so
+        extra += os.environ["MHO_EXTRA_FLAGS"].split()
+        out = os.path.join(HERE, os.environ.get("MHO_OUT", "libmho_exp.so"))
     cmd = [nvcc()] + NVCC_FLAGS + extra + ["-o", out] + srcs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -35,8 +35,8 @@
 
 // -DMHO_PROBE: CTAs 0 and gridDim.x - 1 record clock64 marks (compute thread 0 and the control lane) and print them
 #ifdef MHO_PROBE
-#define PROBE_C(id) do { if (probe_on && tid == 0 && pn_c < 60) { probe_s[pn_c] = (clock64() << 8) | (long long)(id); ++pn_c; } } while (0)
-#define PROBE_M(id) do { if (probe_on && lane == 0 && pn_m < 60) { probe_s[64 + pn_m] = (clock64() << 8) | (long long)(id); ++pn_m; } } while (0)
+#define PROBE_C(id) do { if (probe_on && tid == 0 && pn_c < 120) { probe_s[pn_c] = (clock64() << 8) | (long long)(id); ++pn_c; } } while (0)
+#define PROBE_M(id) do { if (probe_on && lane == 0 && pn_m < 60) { probe_s[128 + pn_m] = (clock64() << 8) | (long long)(id); ++pn_m; } } while (0)
 #else
 #define PROBE_C(id) do { } while (0)
 #define PROBE_M(id) do { } while (0)
@@ -45,7 +45,7 @@
 namespace {
 
 constexpr int HF_COMPUTE_THREADS = 256;
-constexpr int HF_THREADS = 288;         // 8 compute warps + the control warp
+constexpr int HF_THREADS = 256;         // 8 compute warps (no dedicated issuer: the last warp to arrive issues the UMMAs)
 constexpr int HF_TILE_BYTES = 128 * 128;  // part tile ([node][h 64 B | l 64 B]), input staging, output staging
 
 struct HfParams {
@@ -55,6 +55,7 @@ struct HfParams {
     const unsigned char* wimg;  // [32 K rows x 128 B: W'_k[o][f] as fp16 h | l][bias row 128 B][header 128 B]
     int act;
     float slope;
+    int stagger;      // clock cycles the second CTA of an SM waits before its first tile (de-phases the two CTAs)
     int use_bits;     // the batch carries adjacency bit rows
     int nnz_cap;      // CSR staging capacity in ints (multiple of 4), 0 with bit rows
     int stage_bytes;  // bytes of one operator staging set (multiple of 16)
@@ -187,8 +188,26 @@ __global__ void __launch_bounds__(256) hf_prepare_weights_kernel(const HfPrepPar
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2): two accumulator columns per instruction
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void bar_quadrant(int q) {   // the two warps of one TMEM lane quadrant (immediate barrier ids 2..5)
+    if (q == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else if (q == 1) asm volatile("bar.sync 3, 64;" ::: "memory");
+    else if (q == 2) asm volatile("bar.sync 4, 64;" ::: "memory");
+    else asm volatile("bar.sync 5, 64;" ::: "memory");
+}
+
+// One tile in flight per CTA, two CTAs per SM (K <= 5; one CTA with 512 tensor-memory columns for K > 5).  Per tile:
+//   [end of the previous tile: arrive for this tile's X W group - its part tile was written a tile ago]
+//   epilogue of the previous tile and this tile's adjacency expansion run under the X W group;
+//   X W done -> scales, B_K-1 = P_K-1 / row scale, split, arrive;   next tile's input rows are split into the OTHER part
+//   tile inside the wait window of a Clenshaw step;   steps k = K-2 .. 0: wait, LDTM, recurrence (packed fp32), split, arrive.
 template <int K, bool TRACK>
-__global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParams p) {
+__global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(const __grid_constant__ HfParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int W_BYTES = hf_w_bytes(K);
     constexpr uint32_t TCOLS = (K <= 5) ? 256u : 512u;
@@ -196,58 +215,80 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef MHO_PROBE
-    __shared__ long long probe_s[128];
+    __shared__ long long probe_s[192];
     const bool probe_on = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1;
     int pn_c = 0, pn_m = 0;
-    if (tid < 128) probe_s[tid] = 0;
+    if (tid < 192) probe_s[tid] = 0;
     __syncthreads();
     unsigned long long gt0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #endif
     PROBE_C(1);
 
-    // ---- shared memory carve-up
-    unsigned char* parts_s = smem;                         // 16 KB part tile
-    unsigned char* xs_s = smem + HF_TILE_BYTES;            // two 16 KB staging tiles (input rows, then the tile's output rows)
-    unsigned char* w_s = smem + 3 * HF_TILE_BYTES;         // weight image
-    unsigned char* lut_s = w_s + W_BYTES;                  // 256 x 16 B: 8 adjacency bits -> 8 fp16 (0 / 1)
-    unsigned char* ctl_s = lut_s + 4096;                   // 512 B control block
-    unsigned char* mask_s = ctl_s + 512;                   // 2 KB bit rows built from a CSR slice
-    unsigned char* op_s = mask_s + 2048;                   // two operator staging sets
-    const uint32_t parts_a = smem_u32(parts_s), xs_a = smem_u32(xs_s), w_a = smem_u32(w_s), lut_a = smem_u32(lut_s), ctl_a = smem_u32(ctl_s);
-    const uint32_t mask_a = smem_u32(mask_s), op_a = smem_u32(op_s);
+    // ---- shared memory carve-up: two part tiles | two staging tiles | weights | control block | LUT | masks | operator staging
+    unsigned char* w_s = smem + 4 * HF_TILE_BYTES;
+    unsigned char* ctl_s = w_s + W_BYTES;            // 1536 B
+    unsigned char* lut_s = ctl_s + 1536;             // 16 x 8 B: four adjacency bits -> four fp16 (0 / 1)
+    unsigned char* mask_s = lut_s + 128;             // 2 x 2 KB bit rows built from a CSR slice
+    unsigned char* op_s = mask_s + 4096;             // two operator staging sets
+    const uint32_t smem_a = smem_u32(smem), xs_a = smem_a + 2u * HF_TILE_BYTES, w_a = smem_u32(w_s), ctl_a = smem_u32(ctl_s), lut_a = smem_u32(lut_s),
+                   mask_a = smem_u32(mask_s), op_a = smem_u32(op_s);
+    // control block: full[2] +0, empty[2] +16, parts +32, mma +40, tmem slot +48, tile info +64 ([buf][4]), reductions +96 ([3][2]),
+    // running maxima +128 ([3][16]), row scales +512 ([2][128] floats)
     const uint32_t bar_full = ctl_a, bar_empty = ctl_a + 16, bar_parts = ctl_a + 32, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
-    volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);           // [2][4] {node0, rows, nz0, nnz} of the staged tiles
-    unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);            // [2][2] {max |x| bits, max degree} per tile parity
-    unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);         // [2][16] running max |B'_k| bits per tile parity (TRACK)
+    volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);
+    unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
+    unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);
+    float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
 
-    if (warp < 8) {
-        // lookup table: bit j of the index -> fp16 1.0 in half j
-        uint32_t r[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = (((tid >> (2 * j)) & 1) ? 0x3C00u : 0u) | (((tid >> (2 * j + 1)) & 1) ? 0x3C000000u : 0u);
-        sts_u128(lut_a + (uint32_t)tid * 16u, r[0], r[1], r[2], r[3]);
-        if (tid < 64) reinterpret_cast<unsigned int*>(ctl_s + 96)[tid] = 0u;   // red_s and track_s
-    }
+    const int G = (int)gridDim.x;
+    const int n_my = (int)blockIdx.x < p.b.n_tiles ? (p.b.n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+
+    auto issue_load = [&](int j) {   // all of warp 0
+        const int buf = j & 1;
+        const int4 ti = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + j * G));
+        const uint32_t fb = bar_full + 8u * buf;
+        const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
+        if (lane == 0) {
+            tinfo_s[buf * 4 + 0] = ti.x; tinfo_s[buf * 4 + 1] = ti.y; tinfo_s[buf * 4 + 2] = ti.z; tinfo_s[buf * 4 + 3] = ti.w;
+            const uint32_t xb = (uint32_t)ti.y * 128u;
+            mbar_expect_tx(fb, xb + (p.use_bits ? (uint32_t)ti.y * 16u : 0u));
+            bulk_g2s(xs_a + (uint32_t)buf * HF_TILE_BYTES, p.X + (size_t)ti.x * 32, xb, fb);
+            if (p.use_bits) bulk_g2s(opb, p.b.adj_bits + (size_t)ti.x * 4, (uint32_t)ti.y * 16u, fb);
+        }
+        if (!p.use_bits) {
+            // CSR slice: row pointers at opb, column ids 132 ints further (4 B alignment only: cp.async, not a bulk copy)
+            for (int i = lane; i <= ti.y; i += 32) cp_async4(opb + (uint32_t)i * 4u, p.b.rowptr + ti.x + i);
+            for (int e = lane; e < ti.w; e += 32) cp_async4(opb + 528u + (uint32_t)e * 4u, p.b.colidx + ti.z + e);
+            cp_async_mbar_arrive(fb);
+        }
+    };
+
     if (tid == 0) {
-        const uint32_t full_count = p.use_bits ? 1u : 33u;   // expect_tx arrive (+ one cp.async arrive per control lane)
+        const uint32_t full_count = p.use_bits ? 1u : 33u;   // expect_tx arrive (+ one cp.async arrive per lane of warp 0)
         mbar_init(bar_full, full_count);
         mbar_init(bar_full + 8, full_count);
         mbar_init(bar_empty, 8);
         mbar_init(bar_empty + 8, 8);
         mbar_init(bar_parts, 8);
         mbar_init(bar_mma, 1);
+        *reinterpret_cast<volatile unsigned int*>(ctl_s + 56) = 0u;   // arrival counter (MHO_ATOM_ARRIVE builds)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(tslot, TCOLS);
-
-    // from here on global memory written by earlier launches in the stream is read
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (warp < 8) {
-        for (int c = tid; c < W_BYTES / 16; c += HF_COMPUTE_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
-        cp_async_commit();
-        cp_async_wait<0>();
+    if (tid < 16) {
+        const uint32_t x = ((tid & 1) ? 0x3C00u : 0u) | ((tid & 2) ? 0x3C000000u : 0u), y = ((tid & 4) ? 0x3C00u : 0u) | ((tid & 8) ? 0x3C000000u : 0u);
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(lut_a + (uint32_t)tid * 8u), "r"(x), "r"(y) : "memory");
     }
+    if (tid < 104) reinterpret_cast<unsigned int*>(ctl_s + 96)[tid] = 0u;   // reductions and running maxima
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on global memory written by earlier launches in the stream is read
+    if (warp == 0) {
+        __syncwarp();
+        if (n_my > 0) issue_load(0);   // the first tile's loads fly during the rest of the set-up
+        tmem_alloc(tslot, TCOLS);
+    }
+    for (int c = tid; c < W_BYTES / 16; c += HF_COMPUTE_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
+    cp_async_commit();
+    cp_async_wait<0>();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -256,114 +297,61 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
     PROBE_C(2);
     PROBE_M(2);
 
-    const int G = (int)gridDim.x;
-    const int n_my = (int)blockIdx.x < p.b.n_tiles ? (p.b.n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-
-    if (warp == 8) {
-        // =========================== control warp: bulk copies + UMMA issue ===========================
-        auto issue_load = [&](int j) {
-            const int buf = j & 1;
-            const int4 ti = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + j * G));
-            const uint32_t fb = bar_full + 8u * buf;
-            const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
-            if (lane == 0) {
-                tinfo_s[buf * 4 + 0] = ti.x; tinfo_s[buf * 4 + 1] = ti.y; tinfo_s[buf * 4 + 2] = ti.z; tinfo_s[buf * 4 + 3] = ti.w;
-                const uint32_t xb = (uint32_t)ti.y * 128u;
-                mbar_expect_tx(fb, xb + (p.use_bits ? (uint32_t)ti.y * 16u : 0u));
-                bulk_g2s(xs_a + (uint32_t)buf * HF_TILE_BYTES, p.X + (size_t)ti.x * 32, xb, fb);
-                if (p.use_bits) bulk_g2s(opb, p.b.adj_bits + (size_t)ti.x * 4, (uint32_t)ti.y * 16u, fb);
-            }
-            if (!p.use_bits) {
-                // CSR slice: row pointers at opb, column ids 132 ints further (4 B alignment only: cp.async, not a bulk copy)
-                for (int i = lane; i <= ti.y; i += 32) cp_async4(opb + (uint32_t)i * 4u, p.b.rowptr + ti.x + i);
-                for (int e = lane; e < ti.w; e += 32) cp_async4(opb + 528u + (uint32_t)e * 4u, p.b.colidx + ti.z + e);
-                cp_async_mbar_arrive(fb);
-            }
-        };
-        uint32_t ph_parts = 0;
-        if (n_my > 0) issue_load(0);
-        for (int j = 0; j < n_my; ++j) {
-            if (j + 1 < n_my) {
-                if (j + 1 >= 2) {   // tile j - 1 (same buffer) has stored its output rows
-                    if (lane == 0) mbar_wait(bar_empty + 8u * ((j + 1) & 1), (uint32_t)((((j + 1) >> 1) + 1) & 1));
-                    __syncwarp();
-                }
-                issue_load(j + 1);
-            }
-            if (lane == 0) {
-                // ---- P = X' [W'_0 | ... | W'_K-1]: (l h), (h l), (h h) part products, two 16-wide K steps each
-                PROBE_M(10);
-                mbar_wait(bar_parts, ph_parts);
-                ph_parts ^= 1u;
-                tc_fence_after();
-                PROBE_M(11);
-#pragma unroll
-                for (int g = 0; g < (K + 4) / 5; ++g) {
-                    const int nb = (K - 5 * g) < 5 ? (K - 5 * g) : 5;   // column blocks of this group
-                    const uint32_t d = tmem_base + (uint32_t)(160 * g);
-                    const uint32_t wg = w_a + (uint32_t)(160 * g) * 128u;
-                    const uint32_t id_pos = idesc_f16((uint32_t)(32 * nb), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * nb), 0u, 1u);
-                    // x = xh - xl', w = wh - wl':  x w ~ xh wh - xh wl' - xl' wh
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(wg + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 64u + 32u * ks), id_neg, 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 32u * ks), id_pos, 1u);
-                }
-                umma_commit(bar_mma);
-                PROBE_M(12);
-                // ---- Clenshaw steps: D = A parts(B_k+1) into column blocks k+1 (A h) and k+2 (A l')
-                const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
-#pragma unroll 1
-                for (int k = K - 2; k >= 0; --k) {
-                    mbar_wait(bar_parts, ph_parts);
-                    ph_parts ^= 1u;
-                    tc_fence_after();
-                    PROBE_M(20 + k);
-                    const uint32_t d = tmem_base + (uint32_t)(32 * (k + 1));
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, tmem_base + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
-                    umma_commit(bar_mma);
-                    PROBE_M(30 + k);
-                }
-            }
-            __syncwarp();
-        }
-    } else {
+    {
         // =========================== compute warps ===========================
         const int q = warp & 3, hh = warp >> 2;                 // TMEM lane quadrant, column half
         const uint32_t r = (uint32_t)(q * 32 + lane);           // tile row = TMEM lane
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * hh);
         const uint32_t key = r & 7u;
-        const uint32_t prow_a = parts_a + r * 128u;             // this thread's row of the part tile
         const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
         const float* hdr_s = bias_s + 32;
-        uint32_t ph_mma = 0;
+        const float inv_sw = hdr_s[0];
+        const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
+        uint32_t ph_mma = 0, ph_parts = 0;
+        float b1[16], b2[16];
 
-        for (int j = 0; j < n_my; ++j) {
+        // ---- input rows of tile j -> part tile j & 1 (row-scaled), the tile's maxima via shared-memory atomics.  No arrive.
+        float mx_keep = 0.f;   // tile maximum carried from the first half of a split to the second
+        auto x_split = [&](int j, int part) {   // part 0 / 1: the two halves of the rows; part 2: both
             const int buf = j & 1;
-            const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
-            const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
             PROBE_C(3);
-            mbar_wait(bar_full + 8u * buf, (uint32_t)((j >> 1) & 1));
+            if (part != 1) mbar_wait(bar_full + 8u * buf, (uint32_t)((j >> 1) & 1));
             PROBE_C(4);
             const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1], nz0 = tinfo_s[buf * 4 + 2];
-            unsigned int* red = red_s + 2 * buf;
-
-            // ---- input rows: eight features per thread and pass, linear staging tile (conflict-light 32 B strides)
-            float xin[2][8];
-            float mx = 0.f;
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
+            float mx = part == 1 ? mx_keep : 0.f;
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
+                if (part != 2 && part != pp) continue;
                 const int cp = tid + 256 * pp, row = cp >> 2, q4 = cp & 3;
+                float x[8];
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
                 if (row < rows) { a = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
-                xin[pp][0] = a.x; xin[pp][1] = a.y; xin[pp][2] = a.z; xin[pp][3] = a.w; xin[pp][4] = b.x; xin[pp][5] = b.y; xin[pp][6] = b.z; xin[pp][7] = b.w;
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                float rm = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))), fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 1));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 2));   // the row's maximum (four lanes share a row)
+                mx = fmaxf(mx, rm);
+                int ex = expo_above(rm);                               // row max < 2^ex
+                ex = max(-100, min(110, ex));
+                const float s_row = pow2f(15 - ex);
+                if (q4 == 0) rowscale_s[buf * 128 + row] = pow2f(ex - 15);
+                const uint64_t S2 = pk2(s_row, s_row);
+                uint32_t h[4], l[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(xin[pp][i]));
+                for (int e = 0; e < 4; ++e) {
+                    float y0, y1;
+                    upk2(mul2(pk2(x[2 * e], x[2 * e + 1]), S2), y0, y1);
+                    split2(y0, y1, h[e], l[e]);
+                }
+                const uint32_t ra = parts_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
+                sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
+                sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
             }
-            // ---- operator: max degree of the tile (and, from a CSR slice, the bit rows)
+            if (part == 0) { mx_keep = mx; fence_proxy_async(); return; }
+            // operator: max degree of the tile (and, from a CSR slice, the bit rows)
             unsigned int deg = 0u;
             if (p.use_bits) {
                 if (tid < rows) { const uint4 m4 = lds_u128(opb + (uint32_t)tid * 16u); deg = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w); }
@@ -386,183 +374,291 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
                 m1 |= __shfl_xor_sync(0xffffffffu, m1, 1);
                 m2 |= __shfl_xor_sync(0xffffffffu, m2, 1);
                 m3 |= __shfl_xor_sync(0xffffffffu, m3, 1);
-                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(mask_a + (uint32_t)row * 16u + (uint32_t)sub * 8u), "r"(sub ? m2 : m0), "r"(sub ? m3 : m1) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(mask_a + (uint32_t)buf * 2048u + (uint32_t)row * 16u + (uint32_t)sub * 8u), "r"(sub ? m2 : m0), "r"(sub ? m3 : m1) : "memory");
             }
             {
                 const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
                 const unsigned int wd = __reduce_max_sync(0xffffffffu, deg);
+                unsigned int* red = red_s + (j % 3) * 2;
                 if (lane == 0) { atomicMax(red, wm); atomicMax(red + 1, wd); }
             }
-            PROBE_C(5);
-            bar_compute();
-            PROBE_C(6);
+            fence_proxy_async();   // the part tile is read by the tensor core
+            PROBE_C(7);
+        };
+
+        // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs)
+        auto adjacency = [&](int j) {
+            const int buf = j & 1;
+            const int rows = tinfo_s[buf * 4 + 1];
+            uint2 m2v = make_uint2(0u, 0u);
+            if ((int)r < rows) {
+                const uint32_t src = (p.use_bits ? op_a + (uint32_t)(buf * p.stage_bytes) : mask_a + (uint32_t)buf * 2048u) + r * 16u + (uint32_t)hh * 8u;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m2v.x), "=r"(m2v.y) : "r"(src));
+            }
+#pragma unroll
+            for (int w2 = 0; w2 < 2; ++w2) {
+                const uint32_t m = w2 ? m2v.y : m2v.x;
+                uint32_t aw[16];
+#pragma unroll
+                for (int b4 = 0; b4 < 8; ++b4) {
+                    uint2 v;
+                    const uint32_t idx = b4 == 0 ? ((m << 3) & 0x78u) : ((m >> (4 * b4 - 3)) & 0x78u);
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(lut_a + idx));
+                    aw[2 * b4] = v.x; aw[2 * b4 + 1] = v.y;
+                }
+                tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + ADJ_COL + (uint32_t)(32 * hh + 16 * w2), aw);
+            }
+        };
+
+        // ---- arrive: the warp that arrives last (shared-memory counter, acq_rel) issues the UMMA group itself - no issuer
+        // thread to wake.  `what`: -1 = X W group of the tile whose parts are in part tile `buf`, k >= 0 = Clenshaw step k.
+        auto arrive_issue = [&](int buf, int what, int rows_t) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+#ifdef MHO_ATOM_ARRIVE
+                // relaxed shared-memory counter behind this warp's fences (fence + relaxed atomic = release); the warp that
+                // sees seven earlier arrivals completes the group: acquire fence, then it issues
+                unsigned int old;
+                asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ctl_a + 56) : "memory");
+                if ((old & 7u) == 7u) {
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
+                // arrive (release) on the 8-warp barrier; the state it returns is the one BEFORE this arrive: one pending arrival
+                // left means this warp completes the phase - it issues the group (after an acquire on the completed phase)
+                uint32_t pending;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .b64 st;\n\t"
+                    "mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
+                    "mbarrier.pending_count.b64 %0, st;\n\t"
+                    "}" : "=r"(pending) : "r"(bar_parts) : "memory");
+                if (pending == 1u) {
+                    mbar_wait(bar_parts, ph_parts);   // completed by this very arrive: returns at once, acquires the other warps' writes
+#endif
+                    tc_fence_after();
+                    const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+                    if (what < 0) {
+                        // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh, two 16-wide K steps each
+                        PROBE_M(11);
+#pragma unroll
+                        for (int g = 0; g < (K + 4) / 5; ++g) {
+                            const int nb = (K - 5 * g) < 5 ? (K - 5 * g) : 5;   // column blocks of this group
+                            const uint32_t d = tmem_base + (uint32_t)(160 * g);
+                            const uint32_t wg = w_a + (uint32_t)(160 * g) * 128u;
+                            const uint32_t id_pos = idesc_f16((uint32_t)(32 * nb), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * nb), 0u, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(wg + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 64u + 32u * ks), id_neg, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 32u * ks), id_pos, 1u);
+                        }
+                        umma_commit(bar_mma);
+                        PROBE_M(12);
+                    } else {
+                        // D = A parts(B_k+1) into column blocks k+1 (A h) and k+2 (A l')
+                        PROBE_M(20 + what);
+                        const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
+                        const uint32_t d = tmem_base + (uint32_t)(32 * (what + 1));
+                        const int nks = (rows_t + 15) >> 4;   // 16-node slices beyond the tile's rows are all zero
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            if (ks == 0 || ks < nks) umma_f16_ts(d, tmem_base + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
+                        umma_commit(bar_mma);
+                        PROBE_M(30 + what);
+                    }
+                }
+            }
+            ph_parts ^= 1u;
+            __syncwarp();
+        };
+
+        // split B_k (b1) with tau_k = 2^(15 - (e - 127)) into part tile `buf`, then arrive for Clenshaw step k - 1
+        auto split_arrive = [&](int buf, int e1, int step, int rows_t) {
+            const uint64_t T2 = pk2(__uint_as_float((uint32_t)(269 - e1) << 23), __uint_as_float((uint32_t)(269 - e1) << 23));
+            const uint32_t prow_a = smem_a + (uint32_t)buf * HF_TILE_BYTES + r * 128u;
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float y0, y1;
+                upk2(mul2(pk2(b1[2 * e], b1[2 * e + 1]), T2), y0, y1);
+                split2(y0, y1, h[e], l[e]);
+            }
+            PROBE_C(60);
+            sts_u128(prow_a + (((uint32_t)(2 * hh) ^ key) << 4), h[0], h[1], h[2], h[3]);
+            sts_u128(prow_a + (((uint32_t)(2 * hh + 1) ^ key) << 4), h[4], h[5], h[6], h[7]);
+            sts_u128(prow_a + (((uint32_t)(4 + 2 * hh) ^ key) << 4), l[0], l[1], l[2], l[3]);
+            sts_u128(prow_a + (((uint32_t)(5 + 2 * hh) ^ key) << 4), l[4], l[5], l[6], l[7]);
+            PROBE_C(61);
+            fence_proxy_async();
+            PROBE_C(62);
+            arrive_issue(buf, step, rows_t);
+        };
+
+        if (p.stagger > 0 && (int)blockIdx.x >= (G + 1) / 2) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)p.stagger) { }
+        }
+        if (n_my > 0) {
+            x_split(0, 2);
+            arrive_issue(0, -1, 0);   // (the first tile's bit rows, built by all threads, are read behind the barrier at the top of the tile loop)
+        }
+        for (int j = 0; j < n_my; ++j) {
+            const int buf = j & 1;
+            const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
+            // the tile's maxima are complete: every warp split this tile's rows before it arrived for a later group of the
+            // previous tile, whose completion this thread has waited for (first tile: the barrier below)
+            if (j == 0) bar_compute();
+            unsigned int* red = red_s + (j % 3) * 2;
+            unsigned int* trk = track_s + (j % 3) * 16;
             const float xmax = __uint_as_float(red[0]);
             const float dmax2 = 2.f * (float)red[1];
-            if (tid == 0) {   // re-arm the other parity's slots (their last readers were two tiles ago)
-                red_s[2 * (buf ^ 1)] = 0u; red_s[2 * (buf ^ 1) + 1] = 0u;
-            }
-            if (TRACK && tid < 16) track_s[16 * (buf ^ 1) + tid] = 0u;
-
-            // ---- scales (powers of two): x' = x 2^(15 - ex) with |x'| < 2^15
-            int ex = expo_above(xmax);
-            ex = max(-100, min(110, ex));
-            const float s_x = pow2f(15 - ex);
-            const float inv_S = pow2f(ex - 15) * hdr_s[0];
-            // bounds of |B'_k| (scaled units) -> exponent of tau_k = 2^(15 - E): |B'_k| tau_k < 2^15
-            int eb[K + 1];   // biased exponent fields of the bounds, clamped
+            if (tid == 0) { unsigned int* o = red_s + ((j + 2) % 3) * 2; o[0] = 0u; o[1] = 0u; }   // last read a tile ago, next written a tile ahead
+            if (TRACK && tid < 16) track_s[((j + 2) % 3) * 16 + tid] = 0u;
+            const float inv_si = rowscale_s[buf * 128 + r];
+            int e_tau[K];   // clamped exponent fields of the bounds of |B_k| (units of the weight scale), k = 1 .. K-1
             {
                 float bet1 = 0.f, bet2 = 0.f;
 #pragma unroll
                 for (int k = K - 1; k >= 1; --k) {
-                    const float bet = 32768.f * hdr_s[1 + k] + dmax2 * bet1 + bet2;
-                    int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;   // bet < 2^(e - 127)
-                    eb[k] = max(30, min(240, e));
+                    const float bet = xmax * hdr_s[1 + k] + dmax2 * bet1 + bet2;
+                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;   // bet < 2^(e - 127)
+                    e_tau[k] = max(30, min(240, e));
                     bet2 = bet1;
                     bet1 = bet;
                 }
-                eb[0] = 127; eb[K] = 127;
+                e_tau[0] = 127;
             }
-
-            // ---- split the input rows into the part tile
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int cp = tid + 256 * pp, row = cp >> 2, q4 = cp & 3;
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split2(xin[pp][2 * i] * s_x, xin[pp][2 * i + 1] * s_x, h[i], l[i]);
-                const uint32_t ra = parts_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
-                sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
-                sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
-            }
-            fence_proxy_async();
-            tc_fence_before();   // orders this thread's TMEM reads of the previous tile before the next X W overwrites P
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_parts);
-            PROBE_C(7);
-
-            // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), behind the X W group
-            {
-                uint2 m2v = make_uint2(0u, 0u);
-                if ((int)r < rows) {
-                    const uint32_t src = (p.use_bits ? opb : mask_a) + r * 16u + (uint32_t)hh * 8u;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m2v.x), "=r"(m2v.y) : "r"(src));
+            adjacency(j);
+            if (warp == 0 && j + 1 < n_my) {
+                if (j + 1 >= 2) {   // tile j - 1 (same staging buffer) has stored its output rows
+                    if (lane == 0) mbar_wait(bar_empty + 8u * ((j + 1) & 1), (uint32_t)((((j + 1) >> 1) + 1) & 1));
+                    __syncwarp();
                 }
-#pragma unroll
-                for (int w2 = 0; w2 < 2; ++w2) {
-                    const uint32_t m = w2 ? m2v.y : m2v.x;
-                    uint32_t aw[16];
-#pragma unroll
-                    for (int b8 = 0; b8 < 4; ++b8) {
-                        const uint4 v = lds_u128(lut_a + (((m >> (8 * b8)) & 0xffu) << 4));
-                        aw[4 * b8] = v.x; aw[4 * b8 + 1] = v.y; aw[4 * b8 + 2] = v.z; aw[4 * b8 + 3] = v.w;
-                    }
-                    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + ADJ_COL + (uint32_t)(32 * hh + 16 * w2), aw);
-                }
+                issue_load(j + 1);
             }
 
-            // ---- B_K-1 = P_K-1
+            // ---- X W done -> scales, B_K-1 = P_K-1 / row scale
             PROBE_C(8);
             mbar_wait(bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
             PROBE_C(9);
-            float b1[16], b2[16];
+            const uint64_t I2 = pk2(inv_si, inv_si);
             {
                 uint32_t v[16];
                 tmem_ld16(tmem_row + (uint32_t)(32 * (K - 1)), v);
                 tmem_wait_ld_();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { b1[i] = __uint_as_float(v[i]); b2[i] = 0.f; }
-            }
-            unsigned int* trk = track_s + 16 * buf;
-            if (TRACK) {
                 float m = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) m = fmaxf(m, fabsf(b1[i]));
-                const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                if (lane == 0) atomicMax(trk + (K - 1), wm);
+                for (int e = 0; e < 8; ++e) {
+                    upk2(mul2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), I2), b1[2 * e], b1[2 * e + 1]);
+                    b2[2 * e] = 0.f; b2[2 * e + 1] = 0.f;
+                    if (TRACK) m = fmaxf(m, fmaxf(fabsf(b1[2 * e]), fabsf(b1[2 * e + 1])));
+                }
+                if (TRACK) {
+                    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                    if (lane == 0) atomicMax(trk + (K - 1), wm);
+                }
             }
             tmem_wait_st_();   // the adjacency stores have completed (first read by the first Clenshaw step's UMMAs)
+            split_arrive(buf, e_tau[K - 1], K - 2, rows);
+            PROBE_C(20 + K - 2);
 
             // ---- Clenshaw steps
 #pragma unroll
             for (int k = K - 2; k >= 0; --k) {
-                int e1 = eb[k + 1];   // bound of |B'_k+1|
-                if (TRACK && k + 2 <= K - 1) {
-                    // the maxima of |B'_k+2| (and |B'_k+3|) are complete: their atomics preceded an arrive / wait round
-                    const float m2 = __uint_as_float(trk[k + 2]);
-                    const float m3 = (k + 3 <= K - 1) ? __uint_as_float(trk[k + 3]) : 0.f;
-                    const float bet = 32768.f * hdr_s[1 + k + 1] + dmax2 * m2 + m3;
-                    e1 = max(30, min(240, (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1));
+                // the next tile's input rows are split into the other part tile inside one step's wait window
+                if (K >= 4) {   // two wait windows, half of the rows each
+                    if (k == K - 3 && j + 1 < n_my) x_split(j + 1, 0);
+                    if (k == K - 4 && j + 1 < n_my) x_split(j + 1, 1);
+                } else if (k == (K == 3 ? 1 : 0) && j + 1 < n_my) {
+                    x_split(j + 1, 2);
                 }
-                // tau = 2^(15 - (e1 - 127)): field 127 + 15 + 127 - e1
-                const float tau = __uint_as_float((uint32_t)(269 - e1) << 23);
-                const float cfac = __uint_as_float((uint32_t)(e1 - 15 + (k > 0 ? 1 : 0)) << 23);   // (k > 0 ? 2 : 1) / tau
-                uint32_t h[8], l[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) split2(b1[2 * i] * tau, b1[2 * i + 1] * tau, h[i], l[i]);
-                sts_u128(prow_a + (((uint32_t)(2 * hh) ^ key) << 4), h[0], h[1], h[2], h[3]);
-                sts_u128(prow_a + (((uint32_t)(2 * hh + 1) ^ key) << 4), h[4], h[5], h[6], h[7]);
-                sts_u128(prow_a + (((uint32_t)(4 + 2 * hh) ^ key) << 4), l[0], l[1], l[2], l[3]);
-                sts_u128(prow_a + (((uint32_t)(5 + 2 * hh) ^ key) << 4), l[4], l[5], l[6], l[7]);
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_parts);
-                PROBE_C(20 + k);
-
+                const int e1 = e_tau[k + 1];   // the UMMAs multiplied parts(B_k+1) scaled with tau_k+1
                 mbar_wait(bar_mma, ph_mma);
                 ph_mma ^= 1u;
                 tc_fence_after();
                 PROBE_C(30 + k);
+                const float cfac = __uint_as_float((uint32_t)(e1 - 15 + (k > 0 ? 1 : 0)) << 23);   // (k > 0 ? 2 : 1) / tau_k+1
+                const uint64_t C2 = pk2(cfac, cfac);
                 uint32_t vp[16], vh[16], vl[16];
                 tmem_ld16(tmem_row + (uint32_t)(32 * k), vp);
                 tmem_ld16(tmem_row + (uint32_t)(32 * (k + 1)), vh);
                 tmem_ld16(tmem_row + (uint32_t)(32 * (k + 2)), vl);
                 tmem_wait_ld_();
+                PROBE_C(50 + k);
                 float m = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float bk = fmaf(__uint_as_float(vh[i]) - __uint_as_float(vl[i]), cfac, __uint_as_float(vp[i])) - b2[i];
-                    b2[i] = b1[i];
-                    b1[i] = bk;
-                    if (TRACK) m = fmaxf(m, fabsf(bk));
+                for (int e = 0; e < 8; ++e) {
+                    const uint64_t dv = sub2(pk2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1])), pk2(__uint_as_float(vl[2 * e]), __uint_as_float(vl[2 * e + 1])));
+                    const uint64_t bk = fma2(pk2(__uint_as_float(vp[2 * e]), __uint_as_float(vp[2 * e + 1])), I2, fma2(dv, C2, pk2(-b2[2 * e], -b2[2 * e + 1])));
+                    b2[2 * e] = b1[2 * e]; b2[2 * e + 1] = b1[2 * e + 1];
+                    upk2(bk, b1[2 * e], b1[2 * e + 1]);
+                    if (TRACK) m = fmaxf(m, fmaxf(fabsf(b1[2 * e]), fabsf(b1[2 * e + 1])));
                 }
-                if (TRACK && k > 0) {
-                    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                    if (lane == 0) atomicMax(trk + k, wm);
+                if (k > 0) {
+                    int e0 = e_tau[k];
+                    if (TRACK) {
+                        const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                        if (lane == 0) atomicMax(trk + k, wm);
+                        // the maxima of |B_k+1| and |B_k+2| are complete (their atomics preceded the arrive / UMMA / wait round of
+                        // this step): tighter bound of |B_k| than the a-priori one
+                        const float m1 = __uint_as_float(trk[k + 1]);
+                        const float m2 = (k + 2 <= K - 1) ? __uint_as_float(trk[k + 2]) : 0.f;
+                        const float bet = xmax * hdr_s[1 + k] + dmax2 * m1 + m2;
+                        e0 = max(30, min(240, (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1));
+                        e_tau[k] = e0;
+                    }
+                    split_arrive(buf, e0, k - 1, rows);
+                    PROBE_C(20 + k - 1);
                 }
             }
+            // ---- the next tile's X W group may start: its part tile was written inside this tile, P is consumed
+            if (j + 1 < n_my) arrive_issue(buf ^ 1, -1, 0);
 
-            PROBE_C(40);
             // ---- epilogue: unscale, bias, activation; output rows through the staging tile as whole 128 B lines
+            PROBE_C(40);
             {
+                const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+                const uint64_t W2 = pk2(inv_sw, inv_sw);
                 float y[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] = fmaf(b1[i], inv_S, bias_s[16 * hh + i]);
+                for (int c = 0; c < 4; ++c) {
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 16 * hh + 4 * c);
+                    upk2(fma2(pk2(b1[4 * c], b1[4 * c + 1]), W2, pk2(bv.x, bv.y)), y[4 * c], y[4 * c + 1]);
+                    upk2(fma2(pk2(b1[4 * c + 2], b1[4 * c + 3]), W2, pk2(bv.z, bv.w)), y[4 * c + 2], y[4 * c + 3]);
+                }
                 if (p.act == MHO_ACT_RELU) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+                    for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], 0.f);
+                } else if (leaky_max) {
+                    const uint64_t SL2 = pk2(p.slope, p.slope);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float s0, s1;
+                        upk2(mul2(pk2(y[2 * e], y[2 * e + 1]), SL2), s0, s1);
+                        y[2 * e] = fmaxf(y[2 * e], s0); y[2 * e + 1] = fmaxf(y[2 * e + 1], s1);
+                    }
                 } else if (p.act == MHO_ACT_LEAKY) {
                     const float sl = p.slope;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = y[i] > 0.f ? y[i] : sl * y[i];
+                    for (int e = 0; e < 16; ++e) y[e] = y[e] > 0.f ? y[e] : sl * y[e];
                 }
                 const uint32_t ya = xb_a + r * 128u;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) sts_f128(ya + (((uint32_t)(4 * hh + c) ^ key) << 4), make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]));
-            }
-            bar_compute();
-            {
+                bar_quadrant(q);   // the two warps of this lane quadrant hold all 32 columns of its rows
                 float* dst = p.Y + (size_t)node0 * 32;
 #pragma unroll
                 for (int pp = 0; pp < 4; ++pp) {
-                    const uint32_t c = (uint32_t)tid + 256u * pp, row = c >> 3, ch = c & 7u;
+                    const uint32_t row = (uint32_t)(32 * q + 16 * hh + 4 * pp) + ((uint32_t)lane >> 3), ch = (uint32_t)lane & 7u;
                     if ((int)row < rows) *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = lds_f128(xb_a + row * 128u + ((ch ^ (row & 7u)) << 4));
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8u * buf);   // the staging buffer may be refilled
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8u * buf);   // the staging buffer may be refilled
             PROBE_C(41);
         }
     }
@@ -573,9 +669,9 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
         printf("cta %d tiles %d globaltimer start %llu end +%llu ns\n", (int)blockIdx.x, n_my, gt0, gt1 - gt0);
         const long long base = probe_s[0] >> 8;
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 192; ++i) {
             if (probe_s[i] == 0) continue;
-            printf("cta %d %s id %2d  t %7lld\n", (int)blockIdx.x, i < 64 ? "C" : "M", (int)(probe_s[i] & 255), (probe_s[i] >> 8) - base);
+            printf("cta %d %s id %2d  t %7lld\n", (int)blockIdx.x, i < 128 ? "C" : "M", (int)(probe_s[i] & 255), (probe_s[i] >> 8) - base);
         }
     }
 #endif
@@ -583,7 +679,7 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, TCOLS);
+    if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // ---- ping-pong kernel: one CTA per SM, TWO tiles in flight -------------------------------------------------------------
@@ -600,8 +696,6 @@ __global__ void __maxnreg__(112) cheb_f16_kernel(const __grid_constant__ HfParam
 //   * the first tile's loads are issued before the set-up barrier; output rows go out per lane quadrant (64-thread barrier).
 constexpr int PP_THREADS = 320;   // 8 compute warps + one control warp per slot
 
-__device__ __forceinline__ void bar_quadrant(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
-
 template <int K, bool TRACK>
 __global__ void __launch_bounds__(PP_THREADS, 1) cheb_f16pp_kernel(const __grid_constant__ HfParams p) {
     static_assert(K >= 2 && K <= 5, "two slots of 256 tensor-memory columns");
@@ -611,10 +705,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) cheb_f16pp_kernel(const __grid_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef MHO_PROBE
-    __shared__ long long probe_s[128];
+    __shared__ long long probe_s[192];
     const bool probe_on = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1;
     int pn_c = 0, pn_m = 0;
-    if (tid < 128) probe_s[tid] = 0;
+    if (tid < 192) probe_s[tid] = 0;
     __syncthreads();
     unsigned long long gt0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
@@ -1045,9 +1139,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) cheb_f16pp_kernel(const __grid_
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
         printf("cta %d tiles %d globaltimer start %llu end +%llu ns\n", (int)blockIdx.x, n_my, gt0, gt1 - gt0);
         const long long base = probe_s[0] >> 8;
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 192; ++i) {
             if (probe_s[i] == 0) continue;
-            printf("cta %d %s id %2d  t %7lld\n", (int)blockIdx.x, i < 64 ? "C" : "M", (int)(probe_s[i] & 255), (probe_s[i] >> 8) - base);
+            printf("cta %d %s id %2d  t %7lld\n", (int)blockIdx.x, i < 128 ? "C" : "M", (int)(probe_s[i] & 255), (probe_s[i] >> 8) - base);
         }
     }
 #endif
@@ -1121,7 +1215,7 @@ static size_t hf_smem_bytes(int K, bool has_bits, int max_tile_nnz, int* stage_b
     const int nnz_cap = has_bits ? 0 : ((max_tile_nnz + 3) & ~3);
     const int stage = has_bits ? 2048 : ((528 + nnz_cap * 4 + 15) & ~15);
     if (stage_bytes) *stage_bytes = stage;
-    return (size_t)3 * HF_TILE_BYTES + (size_t)hf_w_bytes(K) + 4096 + 512 + 2048 + (size_t)2 * stage;
+    return (size_t)4 * HF_TILE_BYTES + (size_t)hf_w_bytes(K) + 1536 + 128 + 4096 + (size_t)2 * stage;
 }
 
 bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, bool has_saved, int max_tile_rows,
@@ -1156,13 +1250,17 @@ cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int 
     p.act = fp.layers[0].act;
     p.slope = fp.layers[0].slope;
     p.use_bits = fp.b.adj_bits != nullptr ? 1 : 0;
+    static int stagger_env = -1;
+    if (stagger_env < 0) { const char* e = getenv("MHO_STAGGER"); stagger_env = e ? atoi(e) : 0; }
+    p.stagger = stagger_env;
     const int K = fp.layers[0].K;
     int stage = 0;
-    static int track_env = -1, v2_env = -1;
+    static int track_env = -1, v2_env = -1, pp_env = -1;
+    if (pp_env < 0) { const char* e = getenv("MHO_F16_PP"); pp_env = e ? atoi(e) : 0; }          // 1: experimental ping-pong variant (one CTA per SM)
     if (track_env < 0) { const char* e = getenv("MHO_TRACK"); track_env = e ? atoi(e) : 0; }   // 1: running-maximum scales for every K
     if (v2_env < 0) { const char* e = getenv("MHO_F16_V2"); v2_env = e ? atoi(e) : 0; }         // 1: one tile per CTA, two CTAs per SM
     p.nnz_cap = p.use_bits ? 0 : ((max_tile_nnz + 3) & ~3);
-    if (K <= 5 && !v2_env && pp_smem_bytes(K, p.use_bits != 0, max_tile_nnz, nullptr) <= (size_t)max_smem_optin) {
+    if (K <= 5 && pp_env && !v2_env && pp_smem_bytes(K, p.use_bits != 0, max_tile_nnz, nullptr) <= (size_t)max_smem_optin) {
         const size_t smem_pp = pp_smem_bytes(K, p.use_bits != 0, max_tile_nnz, &stage);
         p.stage_bytes = stage;
         int grid = std::min(num_sms, std::max(1, p.b.n_tiles));
