@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                    mask_a = smem_u32(mask_s), op_a = smem_u32(op_s);
     // control block: full[2] +0, empty[2] +16, parts +32, mma +40, tmem slot +48, tile info +64 ([buf][4]), reductions +96 ([3][2]),
     // running maxima +128 ([3][16]), row scales +512 ([2][128] floats)
-    const uint32_t bar_full = ctl_a, bar_empty = ctl_a + 16, bar_parts = ctl_a + 32, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
+    const uint32_t bar_full = ctl_a, bar_empty = ctl_a + 16, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
     volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);
     unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
     unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);
@@ -270,9 +270,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         mbar_init(bar_full + 8, full_count);
         mbar_init(bar_empty, 8);
         mbar_init(bar_empty + 8, 8);
-        mbar_init(bar_parts, 8);
         mbar_init(bar_mma, 1);
-        *reinterpret_cast<volatile unsigned int*>(ctl_s + 56) = 0u;   // arrival counter (MHO_ATOM_ARRIVE builds)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) {
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         const float* hdr_s = bias_s + 32;
         const float inv_sw = hdr_s[0];
         const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
-        uint32_t ph_mma = 0, ph_parts = 0;
+        uint32_t ph_mma = 0;
         float b1[16], b2[16];
 
         // ---- input rows of tile j -> part tile j & 1 (row-scaled), the tile's maxima via shared-memory atomics.  No arrive.
@@ -410,68 +408,54 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             }
         };
 
-        // ---- arrive: the warp that arrives last (shared-memory counter, acq_rel) issues the UMMA group itself - no issuer
-        // thread to wake.  `what`: -1 = X W group of the tile whose parts are in part tile `buf`, k >= 0 = Clenshaw step k.
+        // ---- all warps have written their parts -> thread 0 issues the UMMA group.
+        // `what`: -1 = X W group of the tile whose parts are in part tile `buf`, k >= 0 = Clenshaw step k.
         auto arrive_issue = [&](int buf, int what, int rows_t) {
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-#ifdef MHO_ATOM_ARRIVE
-                // relaxed shared-memory counter behind this warp's fences (fence + relaxed atomic = release); the warp that
-                // sees seven earlier arrivals completes the group: acquire fence, then it issues
-                unsigned int old;
-                asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ctl_a + 56) : "memory");
-                if ((old & 7u) == 7u) {
-                    asm volatile("fence.acq_rel.cta;" ::: "memory");
-#else
-                // arrive (release) on the 8-warp barrier; the state it returns is the one BEFORE this arrive: one pending arrival
-                // left means this warp completes the phase - it issues the group (after an acquire on the completed phase)
-                uint32_t pending;
-                asm volatile(
-                    "{\n\t"
-                    ".reg .b64 st;\n\t"
-                    "mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
-                    "mbarrier.pending_count.b64 %0, st;\n\t"
-                    "}" : "=r"(pending) : "r"(bar_parts) : "memory");
-                if (pending == 1u) {
-                    mbar_wait(bar_parts, ph_parts);   // completed by this very arrive: returns at once, acquires the other warps' writes
-#endif
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            if (what < 0) {
+                // X W group: the A operand is all 128 rows -> hardware barrier over the 8 warps, then a fixed thread issues (the
+                // barrier unit answers within a few tens of cycles; an mbarrier arrive that returns its state, or waking a
+                // dedicated issuer warp, costs 150-200)
+                bar_compute();
+                if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
-                    if (what < 0) {
-                        // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh, two 16-wide K steps each
-                        PROBE_M(11);
+                    // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh, two 16-wide K steps each
+                    PROBE_M(11);
 #pragma unroll
-                        for (int g = 0; g < (K + 4) / 5; ++g) {
-                            const int nb = (K - 5 * g) < 5 ? (K - 5 * g) : 5;   // column blocks of this group
-                            const uint32_t d = tmem_base + (uint32_t)(160 * g);
-                            const uint32_t wg = w_a + (uint32_t)(160 * g) * 128u;
-                            const uint32_t id_pos = idesc_f16((uint32_t)(32 * nb), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * nb), 0u, 1u);
+                    for (int g = 0; g < (K + 4) / 5; ++g) {
+                        const int nb = (K - 5 * g) < 5 ? (K - 5 * g) : 5;   // column blocks of this group
+                        const uint32_t d = tmem_base + (uint32_t)(160 * g);
+                        const uint32_t wg = w_a + (uint32_t)(160 * g) * 128u;
+                        const uint32_t id_pos = idesc_f16((uint32_t)(32 * nb), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * nb), 0u, 1u);
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(wg + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(wg + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 64u + 32u * ks), id_neg, 1u);
+                        for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 64u + 32u * ks), id_neg, 1u);
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 32u * ks), id_pos, 1u);
-                        }
-                        umma_commit(bar_mma);
-                        PROBE_M(12);
-                    } else {
-                        // D = A parts(B_k+1) into column blocks k+1 (A h) and k+2 (A l')
-                        PROBE_M(20 + what);
-                        const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
-                        const uint32_t d = tmem_base + (uint32_t)(32 * (what + 1));
-                        const int nks = (rows_t + 15) >> 4;   // 16-node slices beyond the tile's rows are all zero
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            if (ks == 0 || ks < nks) umma_f16_ts(d, tmem_base + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
-                        umma_commit(bar_mma);
-                        PROBE_M(30 + what);
+                        for (int ks = 0; ks < 2; ++ks) umma_f16_ss(d, desc_sw128(parts_a + 32u * ks), desc_sw128(wg + 32u * ks), id_pos, 1u);
                     }
+                    umma_commit(bar_mma);
+                    PROBE_M(12);
+                }
+            } else {
+                // Clenshaw step: D = A parts(B_k+1) into column blocks k+1 (A h) and k+2 (A l').  (Measured and rejected: one issuer
+                // per lane quadrant behind 64-thread barriers with an ordering flag - four commits and the flag polls cost more
+                // than the parallel issue wins.)
+                bar_compute();
+                if (tid == 0) {
+                    tc_fence_after();
+                    PROBE_M(20 + what);
+                    const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
+                    const uint32_t d = tmem_base + (uint32_t)(32 * (what + 1));
+                    const int nks = (rows_t + 15) >> 4;   // 16-node slices beyond the tile's rows are all zero
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        if (ks == 0 || ks < nks) umma_f16_ts(d, tmem_base + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
+                    umma_commit(bar_mma);
+                    PROBE_M(30 + what);
                 }
             }
-            ph_parts ^= 1u;
-            __syncwarp();
         };
 
         // split B_k (b1) with tau_k = 2^(15 - (e - 127)) into part tile `buf`, then arrive for Clenshaw step k - 1
