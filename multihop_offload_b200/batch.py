@@ -218,9 +218,18 @@ class GraphBatch:
         g0, g1 = bounds[rank], max(bounds[rank], bounds[rank + 1])
         n0, n1 = int(self.graph_off[g0]), int(self.graph_off[g1])
         z0, z1 = int(self.rowptr[n0]), int(self.rowptr[n1])
+        transpose = None
+        if not self.symmetric:
+            # the VJP walks the transposed operator: rebuild it for the shard's block (graphs are block-diagonal, so the
+            # transpose of the slice is the slice of the transpose)
+            import scipy.sparse as sp
+            vals = np.ones(z1 - z0, dtype=np.float32) if self.vals is None else self.vals[z0:z1]
+            At = sp.csr_matrix((vals, self.colidx[z0:z1] - n0, self.rowptr[n0:n1 + 1] - z0), shape=(n1 - n0, n1 - n0)).T.tocsr()
+            At.sort_indices()
+            transpose = (At.indptr.astype(np.int32), At.indices.astype(np.int32), At.data.astype(np.float32))
         sub = GraphBatch(self.graph_off[g0:g1 + 1] - n0, self.rowptr[n0:n1 + 1] - z0, self.colidx[z0:z1] - n0,
                          None if self.vals is None else self.vals[z0:z1], symmetric=self.symmetric,
-                         tile_rows=self.tile_rows)
+                         tile_rows=self.tile_rows, transpose=transpose)
         sub.node_range = (n0, n1)
         sub.graph_range = (g0, g1)
         return sub

@@ -459,6 +459,17 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     const size_t total = al(b_rp) + al(b_ci) + al(b_va) + al(b_ti) + al(b_x) + al(b_y);
     const int slot = (int)(c->host_calls & 1);
     c->host_calls += 1;
+    // an error return below leaves uploads / kernels of this call in flight on the slot's buffers: drain the three streams
+    // before returning so that the next call that recycles the slot cannot overwrite them (the ticket stays -1)
+    struct DrainOnError {
+        mho_ctx* c; cudaStream_t st; bool armed;
+        ~DrainOnError() {
+            if (!armed) return;
+            if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
+            cudaStreamSynchronize(st);
+            if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+        }
+    } drain{c, st, true};
     if (!c->h2d_stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -515,6 +526,7 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
         CUDA_TRY(cudaMemcpyAsync(Y_h + (size_t)n0 * f_out, d_y + (size_t)n0 * f_out, (size_t)(n1 - n0) * f_out * 4, cudaMemcpyDeviceToHost, sd));
     }
     CUDA_TRY(cudaEventRecord(ev_done, sd));
+    drain.armed = false;
     c->slot_used[slot] = true;
     if (ticket) *ticket = slot;
     if (sync) {

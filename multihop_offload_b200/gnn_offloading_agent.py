@@ -272,7 +272,11 @@ class ACOAgent:
         if fused:
             # fused fp64 head kernels (csrc/queue_head.cu); the per-network constants are cached on the device
             hi = qh.HeadInputs(obj, env, None)
-            key = (id(env), hi.link_rates_host.tobytes(), hi.node_mu_host.tobytes(), hi.maps_ol_el_host.tobytes())
+            # every constant the cached device copy holds is part of the key (id(env) is not: ids are recycled)
+            import scipy.sparse as sp_
+            adj_i = sp_.csr_matrix(hi.adj_i_host)
+            key = (hi.link_rates_host.tobytes(), hi.node_mu_host.tobytes(), hi.maps_ol_el_host.tobytes(), hi.maps_on_el_host.tobytes(),
+                   hi.cf_degs_host.tobytes(), adj_i.indptr.tobytes(), adj_i.indices.tobytes(), float(hi.T), int(nn))
             hb = self._head_cache.get(key)
             if hb is None:
                 if len(self._head_cache) > 32:
@@ -280,11 +284,13 @@ class ACOAgent:
                 hb = qh.HeadBatch([hi], [nn], self.net.ctx, self.device)
                 self._head_cache[key] = hb
             ld, nd = hb.forward(lambda_array, save=save)
+            head_tape = hb.last_tape if save else None   # (lam, saved_mu) of THIS call; the HeadBatch itself is shared
             link_delay, node_delay = ld.reshape(-1, 1), nd.reshape(-1, 1)
             lam64 = None
         else:
             hi = qh.HeadInputs(obj, env, self.device)
             hb = None
+            head_tape = None
             lam64 = lambda_array.detach().to(torch.float64)
             if save:
                 lam64.requires_grad_(True)
@@ -294,7 +300,7 @@ class ACOAgent:
                                                      hi.adj_i, hi.T)
         delay_mtx_ts, delay_mtx_np = qh.delay_matrices(link_delay, node_delay, hi, self.bug_compatible)
         if save:
-            self._tape.update(lam64=lam64, link_delay=link_delay, node_delay=node_delay, hi=hi, hb=hb)
+            self._tape.update(lam64=lam64, link_delay=link_delay, node_delay=node_delay, hi=hi, hb=hb, head_tape=head_tape)
         return state, delay_mtx_ts, delay_mtx_np
 
     def _on_gpu(self):
@@ -425,7 +431,7 @@ class ACOAgent:
             raise RuntimeError("no taped forward: call forward(obj, env, save=True) first")
         g_ld, g_nd = qh.seed_from_grad_dist(grad_dist_np, tape["hi"], self.device)
         if tape["hb"] is not None:
-            dY = tape["hb"].backward(g_ld, g_nd).contiguous()
+            dY = tape["hb"].backward(g_ld, g_nd, tape=tape.get("head_tape")).contiguous()
         else:
             (g_lam,) = torch.autograd.grad([tape["link_delay"], tape["node_delay"]], tape["lam64"], [g_ld, g_nd])
             dY = g_lam.to(torch.float32).contiguous()

@@ -89,3 +89,57 @@ def gather_objects(obj, dst=0):
     out = [None] * w if r == dst else None
     dist.gather_object(obj, out, dst=dst)
     return out
+
+
+def bench_exchange(torch, dist_, dev, world_size, barrier, iters=20):
+    """Device-timed cost of AdHoc_train's gradient exchange (the allreduce site of gnn_offloading_agent.py:156-169) on
+    NCCL tensors, for the shipped architecture (3 361 parameters) and its K = 5 variant (16 289): per optimizer step
+      allreduce: ncclAllReduce(SUM) of the flat mean gradient + one mho_adam_replay step;
+      replay:    all-gather of the 10 gradient rows (+ loss / reward) every rank memorised for one file, then the
+                 reference's sequential replay of 100 stored gradients in one mho_adam_replay launch.
+    CUDA events on the current stream, max over ranks.  Returns a dict of microseconds."""
+    from .chebnet import ChebNet, reference_stack
+    from .optim import KerasAdamReplay
+    out = {"n_ranks": world_size, "unit": "us per exchange (CUDA events, max over ranks)"}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / iters], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist_.all_reduce(t, op=dist_.ReduceOp.MAX)
+        return float(t.item())
+
+    for K in (1, 5):
+        net = ChebNet(reference_stack(K=K), device=dev, private_context=True)
+        opt = KerasAdamReplay(net, learning_rate=1e-6)
+        P = net.n_params
+        g1 = torch.randn((1, P), device=dev) * 1e-3
+        rows = torch.randn((10, P), device=dev) * 1e-3
+        meta = torch.zeros((10, 2), device=dev)
+        pool = torch.randn((100, P), device=dev) * 1e-3
+
+        def ar_only():
+            allreduce_mean_(g1)
+
+        def ar_step():
+            allreduce_mean_(g1)
+            opt.apply(g1)
+
+        def gather_only():
+            allgather_rows(rows, meta)
+
+        def replay_step():
+            allgather_rows(rows, meta)
+            opt.apply(pool)
+
+        out["params_%d" % P] = {"allreduce": timed(ar_only), "allreduce_plus_adam_step": timed(ar_step),
+                               "allgather_10_rows_per_rank": timed(gather_only), "allgather_plus_replay_100": timed(replay_step)}
+    return out

@@ -205,20 +205,25 @@ class HeadBatch:
         assert lam.dtype == torch.float32 and lam.numel() == self.total_ext
         ld = torch.empty(self.total_links, dtype=torch.float64, device=self.device)
         nd = torch.empty(self.total_comp, dtype=torch.float64, device=self.device)
-        self.saved_mu = torch.empty(11 * max(self.total_links, 1), dtype=torch.float64, device=self.device) if save else None
+        saved_mu = torch.empty(11 * max(self.total_links, 1), dtype=torch.float64, device=self.device) if save else None
         rc = self.ctx.lib.mho_queue_head_forward(self.ctx.handle, self._C.byref(self.struct), lam.data_ptr(), ld.data_ptr(),
-                                                 nd.data_ptr(), self.saved_mu.data_ptr() if save else None, self._stream())
+                                                 nd.data_ptr(), saved_mu.data_ptr() if save else None, self._stream())
         self._lib.check(rc, "mho_queue_head_forward")
-        self.lam = lam
+        # per-call state of the VJP: the constants of this object are shared (cached per network), so a later forward
+        # (e.g. a save=False evaluation of another instance) must not clobber what a taped forward left behind
+        if save:
+            self.last_tape = (lam, saved_mu)
         return ld, nd
 
-    def backward(self, g_link, g_node):
-        """gradients wrt (link_delay, node_delay) fp64 -> g_lam float32 [total_ext, 1]."""
+    def backward(self, g_link, g_node, tape=None):
+        """gradients wrt (link_delay, node_delay) fp64 -> g_lam float32 [total_ext, 1].  tape = (lam, saved_mu) of the taped
+        forward (default: the last forward(save=True) of this object)."""
+        lam, saved_mu = tape if tape is not None else self.last_tape
         g_link = g_link.reshape(-1).to(torch.float64).contiguous()
         g_node = g_node.reshape(-1).to(torch.float64).contiguous()
         g_lam = torch.empty(self.total_ext, dtype=torch.float32, device=self.device)
-        rc = self.ctx.lib.mho_queue_head_backward(self.ctx.handle, self._C.byref(self.struct), self.lam.data_ptr(),
-                                                  self.saved_mu.data_ptr(), g_link.data_ptr(), g_node.data_ptr(),
+        rc = self.ctx.lib.mho_queue_head_backward(self.ctx.handle, self._C.byref(self.struct), lam.data_ptr(),
+                                                  saved_mu.data_ptr(), g_link.data_ptr(), g_node.data_ptr(),
                                                   g_lam.data_ptr(), self._stream())
         self._lib.check(rc, "mho_queue_head_backward")
         return g_lam.reshape(-1, 1)

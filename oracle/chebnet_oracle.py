@@ -9,7 +9,7 @@ PARITY PINNING: the arithmetic restated here lives in two un-vendored, un-pinned
 third-party packages of the reference (``spektral`` and ``tensorflow``,
 ``src/requirements.txt:9,12``) that cannot be installed in this sandbox, and the
 reference holds no tests or golden outputs for this path.  The oracle is
-therefore pinned *statistically* (``tests/test_statistical_pin.py`` replays the
+therefore pinned *statistically* (``tests/test_agent_host.py::test_statistical_pin_forward_env (30 files) and ::test_statistical_pin_150_files (slow)`` replays the
 reference's AdHoc_test protocol through this oracle + the reference's own
 environment and compares per-size mean tau with the shipped result CSV) and by
 algebraic invariants (Chebyshev polynomials on a diagonal operator, finite

@@ -203,7 +203,8 @@ def test_host_api_multichunk_pipeline_equals_device_api(torch_cuda):
 
 
 def test_weights_change_is_picked_up(torch_cuda):
-    """The packed TF32 weight images are cached per context: set_weights / the optimizer must invalidate them."""
+    """The packed weight images (TF32 hi/lo, bf16 x3, fp16 x2) are cached per context: set_weights must invalidate them
+    (the optimizer: tests/test_f16_kernel_gpu.py::test_forward_after_optimizer_replay_uses_new_weights)."""
     from multihop_offload_b200 import GraphBatch, LayerSpec
     rng = np.random.default_rng(4)
     mats = O.make_batch([40, 50], seed0=1)
@@ -338,7 +339,7 @@ def test_dense_kernel_streams_weights_of_deep_k_stacks(torch_cuda):
         # what plain fp32 arithmetic (numpy) loses on the same stack
         err32 = rel_err(numpy_fp32_forward(mats, X, ws, acts, 0.2), ref, batch.graph_off, zscale)
         print("K", K, "err", err, "numpy-fp32 err", err32)
-        assert err < max(TOL, 3 * err32), (K, err, err32)
+        assert err < max(TOL, 1.5 * err32), (K, err, err32)   # measured table: profiles/r2_deep_stack_errors.json
         h3 = oracle_batch_forward(mats, X, ws[:3], acts[:3], 0.2)
         off = n * (32 + 32)
         got = saved[off: off + n * 32].view(n, 32).cpu().numpy()
