@@ -76,6 +76,11 @@ typedef struct {
        mho_fill_adj_bits).  With it the forward's tensor-core path (vals == NULL, tiles <= 128 nodes) reads 16 B per
        node instead of walking the CSR slice; NULL => the kernel derives the bits from rowptr/colidx itself. */
     const uint32_t* adj_bits;
+    /* optional (device), [n_tiles] parallel to tile_info: index of the FIRST graph of each listed tile (its graphs are
+       consecutive).  With it the fp16-part tensor-core forward scales its operands per GRAPH (graph_off is then read on
+       the device): graphs of very different magnitude may share a tile.  NULL => one scale per tile - exact to 1e-5 as
+       long as the graphs of a tile are within ~2^10 of each other in magnitude. */
+    const int32_t* tile_graph0;
 } mho_batch_t;
 
 /* One ChebConv layer: Y = act(sum_k T_k(A) X W[k] + b), T_0=X, T_1=A X, T_k=2 A T_{k-1}-T_{k-2}

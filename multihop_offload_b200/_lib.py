@@ -21,7 +21,7 @@ class mho_batch_t(C.Structure):
         ("graph_off", C.c_void_p), ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
         ("rowptr_t", C.c_void_p), ("colidx_t", C.c_void_p), ("vals_t", C.c_void_p),
         ("tile_off", C.c_void_p), ("tile_info", C.c_void_p), ("n_tiles", C.c_int32), ("max_tile_rows", C.c_int32),
-        ("max_tile_nnz", C.c_int32), ("adj_bits", C.c_void_p),
+        ("max_tile_nnz", C.c_int32), ("adj_bits", C.c_void_p), ("tile_graph0", C.c_void_p),
     ]
 
 

@@ -134,9 +134,12 @@ class GraphBatch:
         self.n_row_tiles = int(nrt)
         self.max_row_tile_nnz = int(self.row_tile_info[:, 3].max()) if nrt else 0
         # largest tile first: the kernel's CTAs pull tiles in this order from a global counter
+        self.tile_graph0 = self.tile_off[: max(self.n_tiles, 1)].astype(np.int32).copy()   # first graph of each listed tile
         if self.n_tiles > 1:
             cost = 3 * self.tile_info[:, 1].astype(np.int64) + self.tile_info[:, 3]
-            self.tile_info = np.ascontiguousarray(self.tile_info[np.argsort(-cost, kind="stable")])
+            perm = np.argsort(-cost, kind="stable")
+            self.tile_info = np.ascontiguousarray(self.tile_info[perm])
+            self.tile_graph0 = np.ascontiguousarray(self.tile_graph0[perm])
         # one-graph-per-tile statistics (the backward runs one graph per CTA)
         if self.n_graphs:
             sizes = np.diff(self.graph_off)
@@ -157,6 +160,7 @@ class GraphBatch:
 
         self.dev = dict(graph_off=up(self.graph_off), rowptr=up(self.rowptr), colidx=up(self.colidx),
                         tile_off=up(self.tile_off), tile_info=up(self.tile_info), graph_info=up(self.graph_info),
+                        tile_graph0=up(self.tile_graph0),
                         row_tile_info=up(self.row_tile_info))
         if self.vals is not None:
             self.dev["vals"] = up(self.vals)
@@ -203,6 +207,7 @@ class GraphBatch:
             b.tile_info = self.dev["tile_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_tile_rows, self.max_tile_nnz
             b.adj_bits = self.dev["adj_bits"].data_ptr() if "adj_bits" in self.dev else None
+            b.tile_graph0 = self.dev["tile_graph0"].data_ptr() if "tile_graph0" in self.dev else None
         return b
 
     # ---- sharding across ranks (partition by graph, balanced by rows+nnz) ------

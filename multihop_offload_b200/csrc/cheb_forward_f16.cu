@@ -194,6 +194,18 @@ __device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// number of graph-start marks in rows 1 .. row (128 flag bits): the index of the row's graph inside its tile
+__device__ __forceinline__ int group_of(const unsigned int* flags, int row) {
+    const uint4 f = *reinterpret_cast<const uint4*>(flags);
+    const int w = row >> 5;
+    const unsigned int below = (2u << (row & 31)) - 1u;   // bits 0 .. row & 31 (row & 31 == 31: all ones)
+    int g = __popc((w == 0 ? f.x : w == 1 ? f.y : w == 2 ? f.z : f.w) & below);
+    g += w > 0 ? __popc(f.x) : 0;
+    g += w > 1 ? __popc(f.y) : 0;
+    g += w > 2 ? __popc(f.z) : 0;
+    return g;
+}
+
 __device__ __forceinline__ void bar_quadrant(int q) {   // the two warps of one TMEM lane quadrant (immediate barrier ids 2..5)
     if (q == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
     else if (q == 1) asm volatile("bar.sync 3, 64;" ::: "memory");
@@ -231,6 +243,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     unsigned char* lut_s = ctl_s + 1536;             // 16 x 8 B: four adjacency bits -> four fp16 (0 / 1)
     unsigned char* mask_s = lut_s + 128;             // 2 x 2 KB bit rows built from a CSR slice
     unsigned char* op_s = mask_s + 4096;             // two operator staging sets
+    unsigned char* grp_s = op_s + 2 * p.stage_bytes; // per-graph scales: [2][132] graph starts, [3][4] start flags, [3][128] max |x|, [3][128] max degree
     const uint32_t smem_a = smem_u32(smem), xs_a = smem_a + 2u * HF_TILE_BYTES, w_a = smem_u32(w_s), ctl_a = smem_u32(ctl_s), lut_a = smem_u32(lut_s),
                    mask_a = smem_u32(mask_s), op_a = smem_u32(op_s);
     // control block: full[2] +0, empty[2] +16, parts +32, mma +40, tmem slot +48, tile info +64 ([buf][4]), reductions +96 ([3][2]),
@@ -240,13 +253,32 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
     unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);
     float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
+    const uint32_t gb_a = smem_u32(grp_s);                                          // graph starts of the staged tiles
+    unsigned int* gflag_s = reinterpret_cast<unsigned int*>(grp_s + 1056);          // bit r set: a graph starts at tile row r
+    unsigned int* gmax_s = reinterpret_cast<unsigned int*>(grp_s + 1056 + 64);      // max |x| (float bits) per graph of the tile
+    unsigned int* gdeg_s = gmax_s + 3 * 128;                                        // max degree per graph of the tile
+    const bool groups = p.b.tile_graph0 != nullptr;
 
     const int G = (int)gridDim.x;
     const int n_my = (int)blockIdx.x < p.b.n_tiles ? (p.b.n_tiles - (int)blockIdx.x + G - 1) / G : 0;
 
+    // tile descriptors are fetched one tile ahead (registers of warp 0): the loads that depend on them - the bulk copies, the
+    // graph starts - are issued without waiting for global memory
+    int4 ti_pref = make_int4(0, 0, 0, 0);
+    int g0_pref = 0, pref_j = -1;
+    auto prefetch_desc = [&](int j) {
+        if (j < n_my) {
+            ti_pref = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + j * G));
+            if (groups) g0_pref = __ldg(p.b.tile_graph0 + ((int)blockIdx.x + j * G));
+            pref_j = j;
+        }
+    };
     auto issue_load = [&](int j) {   // all of warp 0
         const int buf = j & 1;
-        const int4 ti = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + j * G));
+        if (pref_j != j) prefetch_desc(j);
+        const int4 ti = ti_pref;
+        const int g0 = g0_pref;
+        prefetch_desc(j + 1);
         const uint32_t fb = bar_full + 8u * buf;
         const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
         if (lane == 0) {
@@ -260,12 +292,19 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             // CSR slice: row pointers at opb, column ids 132 ints further (4 B alignment only: cp.async, not a bulk copy)
             for (int i = lane; i <= ti.y; i += 32) cp_async4(opb + (uint32_t)i * 4u, p.b.rowptr + ti.x + i);
             for (int e = lane; e < ti.w; e += 32) cp_async4(opb + 528u + (uint32_t)e * 4u, p.b.colidx + ti.z + e);
-            cp_async_mbar_arrive(fb);
         }
+        if (groups) {
+            // node offsets of the graphs that follow the tile's first one (at most 128 start inside a 128-row tile)
+            for (int e = lane; e < 128; e += 32) {
+                const int gi = min(g0 + 1 + e, p.b.n_graphs);   // graph_off[n_graphs] = total_nodes: beyond every tile
+                cp_async4(gb_a + (uint32_t)(buf * 132 + e) * 4u, p.b.graph_off + gi);
+            }
+        }
+        if (!p.use_bits || groups) cp_async_mbar_arrive(fb);
     };
 
     if (tid == 0) {
-        const uint32_t full_count = p.use_bits ? 1u : 33u;   // expect_tx arrive (+ one cp.async arrive per lane of warp 0)
+        const uint32_t full_count = (p.use_bits && !groups) ? 1u : 33u;   // expect_tx arrive (+ one cp.async arrive per lane of warp 0)
         mbar_init(bar_full, full_count);
         mbar_init(bar_full + 8, full_count);
         mbar_init(bar_empty, 8);
@@ -278,6 +317,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(lut_a + (uint32_t)tid * 8u), "r"(x), "r"(y) : "memory");
     }
     if (tid < 104) reinterpret_cast<unsigned int*>(ctl_s + 96)[tid] = 0u;   // reductions and running maxima
+    for (int i = tid; i < 16 + 6 * 128; i += HF_COMPUTE_THREADS) gflag_s[i] = 0u;   // graph-start flags, per-graph maxima
     asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on global memory written by earlier launches in the stream is read
     if (warp == 0) {
         __syncwarp();
@@ -319,6 +359,16 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
             const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
             const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
+            unsigned int* gflag = gflag_s + (j % 3) * 4;
+            if (groups && part != 1) {
+                // mark the rows at which a graph starts (the flags were cleared a tile ago), then every thread counts the
+                // marks up to its row: the index of its graph inside the tile
+                if (tid < 128) {
+                    const int bnd = (int)lds_u32(gb_a + (uint32_t)(buf * 132 + tid) * 4u) - node0;
+                    if (bnd > 0 && bnd < rows) atomicOr(gflag + (bnd >> 5), 1u << (bnd & 31));
+                }
+                bar_compute();
+            }
             float mx = part == 1 ? mx_keep : 0.f;
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
@@ -335,7 +385,10 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                 int ex = expo_above(rm);                               // row max < 2^ex
                 ex = max(-100, min(110, ex));
                 const float s_row = pow2f(15 - ex);
-                if (q4 == 0) rowscale_s[buf * 128 + row] = pow2f(ex - 15);
+                if (q4 == 0) {
+                    rowscale_s[buf * 128 + row] = pow2f(ex - 15);
+                    if (groups) atomicMax(gmax_s + (j % 3) * 128 + group_of(gflag, row), __float_as_uint(rm));
+                }
                 const uint64_t S2 = pk2(s_row, s_row);
                 uint32_t h[4], l[4];
 #pragma unroll
@@ -379,6 +432,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                 const unsigned int wd = __reduce_max_sync(0xffffffffu, deg);
                 unsigned int* red = red_s + (j % 3) * 2;
                 if (lane == 0) { atomicMax(red, wm); atomicMax(red + 1, wd); }
+                if (groups && deg > 0u) atomicMax(gdeg_s + (j % 3) * 128 + group_of(gflag, p.use_bits ? tid : (tid >> 1)), deg);
             }
             fence_proxy_async();   // the part tile is read by the tensor core
             PROBE_C(7);
@@ -496,10 +550,21 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             if (j == 0) bar_compute();
             unsigned int* red = red_s + (j % 3) * 2;
             unsigned int* trk = track_s + (j % 3) * 16;
-            const float xmax = __uint_as_float(red[0]);
-            const float dmax2 = 2.f * (float)red[1];
+            float xmax = __uint_as_float(red[0]);
+            float dmax2 = 2.f * (float)red[1];
+            const float xmax_tile = xmax, dmax2_tile = dmax2;
+            (void)xmax_tile; (void)dmax2_tile;
+            if (groups) {   // the graph of this thread's row: block-diagonal operator => its own scale per step
+                const int g = group_of(gflag_s + (j % 3) * 4, (int)r);
+                xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
+                dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
+            }
             if (tid == 0) { unsigned int* o = red_s + ((j + 2) % 3) * 2; o[0] = 0u; o[1] = 0u; }   // last read a tile ago, next written a tile ahead
             if (TRACK && tid < 16) track_s[((j + 2) % 3) * 16 + tid] = 0u;
+            if (groups) {
+                if (tid < 4) gflag_s[((j + 2) % 3) * 4 + tid] = 0u;
+                if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
+            }
             const float inv_si = rowscale_s[buf * 128 + r];
             int e_tau[K];   // clamped exponent fields of the bounds of |B_k| (units of the weight scale), k = 1 .. K-1
             {
@@ -591,8 +656,8 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                         // this step): tighter bound of |B_k| than the a-priori one
                         const float m1 = __uint_as_float(trk[k + 1]);
                         const float m2 = (k + 2 <= K - 1) ? __uint_as_float(trk[k + 2]) : 0.f;
-                        const float bet = xmax * hdr_s[1 + k] + dmax2 * m1 + m2;
-                        e0 = max(30, min(240, (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1));
+                        const float bet = xmax_tile * hdr_s[1 + k] + dmax2_tile * m1 + m2;   // tile-wide: bounds every graph of the tile
+                        e0 = min(e0, max(30, min(240, (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1)));
                         e_tau[k] = e0;
                     }
                     split_arrive(buf, e0, k - 1, rows);
@@ -1199,15 +1264,17 @@ static size_t hf_smem_bytes(int K, bool has_bits, int max_tile_nnz, int* stage_b
     const int nnz_cap = has_bits ? 0 : ((max_tile_nnz + 3) & ~3);
     const int stage = has_bits ? 2048 : ((528 + nnz_cap * 4 + 15) & ~15);
     if (stage_bytes) *stage_bytes = stage;
-    return (size_t)4 * HF_TILE_BYTES + (size_t)hf_w_bytes(K) + 1536 + 128 + 4096 + (size_t)2 * stage;
+    return (size_t)4 * HF_TILE_BYTES + (size_t)hf_w_bytes(K) + 1536 + 128 + 4096 + (size_t)2 * stage + 1056 + 64 + 6 * 512;
 }
 
-bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, bool has_saved, int max_tile_rows,
-                       int max_tile_nnz, const void* X, const void* Y, const void* bits, int max_smem_optin) {
+bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, bool has_bits, bool has_saved, bool has_graph_starts,
+                       int max_tile_rows, int max_tile_nnz, const void* X, const void* Y, const void* bits, int max_smem_optin) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MHO_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg & (32 | 64)) return false;   // MHO_DEBUG & 64: keep the first-generation dense kernel; & 32: the CSR-walk kernel
-    if (n_layers != 1 || has_vals || has_saved || max_tile_rows > 128) return false;
+    // one scale per tile is exact to 1e-5 only while tile mates stay within ~2^7 of each other in magnitude at every Clenshaw
+    // step: without the graph starts (mho_batch_t.tile_graph0) the batch goes to the bf16 x 3 kernel, which needs no scales
+    if (n_layers != 1 || has_vals || has_saved || !has_graph_starts || max_tile_rows > 128) return false;
     const mho_layer_t& L = layers[0];
     if (L.f_in != 32 || L.f_out != 32 || L.K < 2 || L.K > 10) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15u) || (reinterpret_cast<uintptr_t>(Y) & 15u) || (reinterpret_cast<uintptr_t>(bits) & 15u)) return false;

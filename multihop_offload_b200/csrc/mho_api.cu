@@ -325,6 +325,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.b.tile_off = b->tile_off; p.b.n_graphs = b->n_graphs;
     p.b.tile_info = b->tile_info;
     p.b.adj_bits = b->adj_bits;
+    p.b.tile_graph0 = b->tile_graph0;
     p.b.n_tiles = b->tile_off ? b->n_tiles : b->n_graphs;
     p.n_layers = n_layers;
     mho_fill_layers(layers, n_layers, b->total_nodes, p.layers);
@@ -332,8 +333,8 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.sched = c->sched;
     // one 32 -> 32 layer with 2 <= K <= 10 on a binary operator (the benchmark layer): second-generation tensor-core kernel
     if (b->tile_off && b->tile_info &&
-        cheb_f16_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, saved != nullptr, b->max_tile_rows, b->max_tile_nnz, X, Y,
-                          b->adj_bits, c->max_smem_optin)) {
+        cheb_f16_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, saved != nullptr, b->tile_graph0 != nullptr && b->graph_off != nullptr,
+                          b->max_tile_rows, b->max_tile_nnz, X, Y, b->adj_bits, c->max_smem_optin)) {
         rc = ensure_prepared_f16(c, layers[0], p.layers[0], (cudaStream_t)stream);
         if (rc) return rc;
         dbg_check("f16 prepared");
@@ -442,21 +443,34 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
         cn0[k] = tinfo[4 * (size_t)cstart[k]];
         cn1[k] = cstart[k + 1] > cstart[k] ? tinfo[4 * (size_t)(cstart[k + 1] - 1)] + tinfo[4 * (size_t)(cstart[k + 1] - 1) + 1] : cn0[k];
     }
-    // inside every chunk: largest tile first for the kernel's dynamic scheduler (tinfo is consumed in order)
-    for (int k = 0; k < n_chunks; ++k) {
-        struct T4 { int32_t v[4]; };
-        T4* beg = reinterpret_cast<T4*>(tinfo.data()) + cstart[k];
-        T4* end = reinterpret_cast<T4*>(tinfo.data()) + cstart[k + 1];
-        // remember the chunk's extent before reordering
-        std::stable_sort(beg, end, [](const T4& a, const T4& b) { return 3LL * a.v[1] + a.v[3] > 3LL * b.v[1] + b.v[3]; });
+    // inside every chunk: largest tile first for the kernel's dynamic scheduler (tinfo is consumed in order); the index of
+    // each tile's first graph travels with it (per-graph operand scales of the fp16 tensor-core kernel)
+    std::vector<int32_t> tgraph0;
+    if (!all_k1) {
+        struct T5 { int32_t v[4]; int32_t g0; };
+        std::vector<T5> tt((size_t)n_tiles);
+        for (int t = 0; t < n_tiles; ++t) { memcpy(tt[t].v, &tinfo[4 * (size_t)t], 16); tt[t].g0 = tile_off[t]; }
+        for (int k = 0; k < n_chunks; ++k)
+            std::stable_sort(tt.begin() + cstart[k], tt.begin() + cstart[k + 1],
+                             [](const T5& a, const T5& b) { return 3LL * a.v[1] + a.v[3] > 3LL * b.v[1] + b.v[3]; });
+        tgraph0.resize((size_t)n_tiles + 4);
+        for (int t = 0; t < n_tiles; ++t) { memcpy(&tinfo[4 * (size_t)t], tt[t].v, 16); tgraph0[t] = tt[t].g0; }
+    } else {
+        for (int k = 0; k < n_chunks; ++k) {
+            struct T4 { int32_t v[4]; };
+            T4* beg = reinterpret_cast<T4*>(tinfo.data()) + cstart[k];
+            T4* end = reinterpret_cast<T4*>(tinfo.data()) + cstart[k + 1];
+            std::stable_sort(beg, end, [](const T4& a, const T4& b) { return 3LL * a.v[1] + a.v[3] > 3LL * b.v[1] + b.v[3]; });
+        }
     }
 
     const int f_in = layers[0].f_in, f_out = layers[n_layers - 1].f_out;
     const size_t b_rp = (size_t)(total_nodes + 1) * 4, b_ci = (size_t)nnz * 4;
     const size_t b_va = vals_h ? (size_t)nnz * 4 : 0, b_ti = (size_t)n_tiles * 16 + 16;
+    const size_t b_go = tgraph0.empty() ? 0 : (size_t)(n_graphs + 1) * 4, b_tg = tgraph0.empty() ? 0 : (size_t)n_tiles * 4 + 16;
     const size_t b_x = (size_t)total_nodes * f_in * 4, b_y = (size_t)total_nodes * f_out * 4;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total = al(b_rp) + al(b_ci) + al(b_va) + al(b_ti) + al(b_x) + al(b_y);
+    const size_t total = al(b_rp) + al(b_ci) + al(b_va) + al(b_ti) + al(b_go) + al(b_tg) + al(b_x) + al(b_y);
     const int slot = (int)(c->host_calls & 1);
     c->host_calls += 1;
     // an error return below leaves uploads / kernels of this call in flight on the slot's buffers: drain the three streams
@@ -487,6 +501,8 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     int32_t* d_ci = (int32_t*)q; q += al(b_ci);
     float* d_va = vals_h ? (float*)q : nullptr; q += al(b_va);
     int32_t* d_ti = (int32_t*)q; q += al(b_ti);
+    int32_t* d_go = b_go ? (int32_t*)q : nullptr; q += al(b_go);
+    int32_t* d_tg = b_tg ? (int32_t*)q : nullptr; q += al(b_tg);
     float* d_x = (float*)q; q += al(b_x);
     float* d_y = (float*)q;
 
@@ -495,6 +511,10 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     // pending work is the other slot's kernels
     (void)ev_start;
     CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
+    if (d_go) {
+        CUDA_TRY(cudaMemcpyAsync(d_go, goff_h, b_go, cudaMemcpyHostToDevice, sh));
+        CUDA_TRY(cudaMemcpyAsync(d_tg, tgraph0.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, sh));
+    }
 
     // node / nnz extent of each chunk (tiles of a chunk are a contiguous run of graphs)
     auto chunk_nodes = [&](int k, int& n0, int& n1) { n0 = cn0[k]; n1 = cn1[k]; };
@@ -512,7 +532,8 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
         mho_batch_t b;
         memset(&b, 0, sizeof(b));
         b.n_graphs = n_graphs; b.total_nodes = total_nodes; b.total_nnz = nnz;
-        b.graph_off = (const int32_t*)d_rp;  // never dereferenced: tile_info carries the bounds
+        b.graph_off = d_go ? d_go : (const int32_t*)d_rp;  // dereferenced only together with tile_graph0
+        b.tile_graph0 = d_tg ? d_tg + cstart[k] : nullptr;
         b.rowptr = d_rp; b.colidx = d_ci; b.vals = d_va;
         b.tile_off = (const int32_t*)d_ti;   // non-NULL marks "tiled"; bounds again come from tile_info
         b.tile_info = d_ti + 4 * (size_t)cstart[k];

@@ -233,6 +233,7 @@ struct BatchDev {
     const int32_t* tile_off;
     const int32_t* tile_info;  // optional [n_tiles][4] = {node0, rows, nz0, nnz}
     const uint32_t* adj_bits;  // optional [total_nodes][4] binary operator as bit rows (tile-local columns)
+    const int32_t* tile_graph0;  // optional [n_tiles] first graph of each listed tile (per-graph operand scales)
     int n_tiles;
     int n_graphs;
 };

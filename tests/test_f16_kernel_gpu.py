@@ -57,9 +57,9 @@ def test_single_layer_all_orders(torch_cuda, K):
 
 
 def test_magnitudes_and_degenerate_graphs(torch_cuda):
-    """The fp16 parts are scaled per row (X W) and per tile and step (Clenshaw): tiles of very different magnitude, graphs
-    two orders of magnitude apart inside ONE tile, zero rows, all-zero tiles, a star graph (max degree n - 1: the loosest
-    degree bound), a graph without edges, tiny graphs."""
+    """The fp16 parts are scaled per row (X W) and per GRAPH and step (Clenshaw; mho_batch_t.tile_graph0): graphs of wildly
+    different magnitude inside ONE tile, zero rows, all-zero graphs, a star graph (max degree n - 1: the loosest degree
+    bound), a graph without edges, tiny graphs.  Without tile_graph0 the library falls back to the bf16 x 3 kernel."""
     from multihop_offload_b200 import LayerSpec
     rng = np.random.default_rng(7)
 
@@ -72,7 +72,7 @@ def test_magnitudes_and_degenerate_graphs(torch_cuda):
     def path(n):
         return sp.csr_matrix(sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1]))
 
-    mats = [O.ba_adjacency(100, 2, 1), O.ba_adjacency(90, 2, 2),         # two tiles of their own
+    mats = [O.ba_adjacency(50, 2, 1), O.ba_adjacency(60, 2, 2),          # one tile, two graphs
             star(110), path(3), path(2), sp.csr_matrix((40, 40)),         # hub, tiny, edgeless
             O.ba_adjacency(30, 2, 3), O.ba_adjacency(30, 2, 4), O.ba_adjacency(30, 2, 5), O.ba_adjacency(30, 2, 6),
             star(128), O.ba_adjacency(100, 2, 7)]
@@ -82,9 +82,9 @@ def test_magnitudes_and_degenerate_graphs(torch_cuda):
         specs = [LayerSpec(K, 32, 32, O.ACT_LEAKY, 0.2)]
         ws = random_weights(specs, rng)
         X = rng.normal(size=(off[-1], 32))
-        X[off[0]:off[1]] *= 1e-6          # neighbouring tiles nine orders of magnitude apart
+        X[off[0]:off[1]] *= 1e-6          # tile mates nine orders of magnitude apart
         X[off[1]:off[2]] *= 1e+3
-        X[off[9]:off[10]] *= 1e+2         # tile mates (four 30-node graphs) two orders of magnitude apart
+        X[off[9]:off[10]] *= 1e+2
         X[off[6]:off[7]] *= 1e-20         # tiny but normal
         X[off[7]:off[8]] *= 1e+18
         X[off[8]:off[9]] = 0.0            # an all-zero graph
@@ -97,6 +97,18 @@ def test_magnitudes_and_degenerate_graphs(torch_cuda):
             per = [np.abs(Y[off[g]:off[g + 1]] - ref[off[g]:off[g + 1]]).max() / max(np.abs(ref[off[g]:off[g + 1]]).max(), zs[g], 1e-30)
                    for g in range(len(mats))]
             assert max(per) < TOL, (K, bits, ["%d:%.2e" % (g, e) for g, e in enumerate(per) if e >= TOL])
+    # without tile_graph0 the batch takes the first-generation kernel (bf16 x 3 parts, no scales): same answers
+    from multihop_offload_b200 import ChebNet, GraphBatch
+    specs = [LayerSpec(5, 32, 32, O.ACT_LEAKY, 0.2)]
+    ws = random_weights(specs, rng)
+    X = rng.normal(size=(off[-1], 32))
+    X[off[0]:off[1]] *= 30.0
+    ref, zs = oracle_batch_forward(mats, X, ws, [s.act for s in specs], 0.2, return_scale=True)
+    net = ChebNet(specs, device="cuda:0"); net.set_weights(ws)
+    batch = GraphBatch.from_scipy(mats, tile_rows=128, device="cuda:0")
+    batch.dev.pop("tile_graph0", None); batch._struct_cache = {}
+    Y = net.forward(batch, torch_cuda.from_numpy(X.astype(np.float32)).cuda()).cpu().numpy()
+    assert rel_err(Y, ref, batch.graph_off, zs) < TOL
 
 
 def test_weight_magnitudes(torch_cuda):
@@ -184,7 +196,9 @@ def test_forward_after_optimizer_replay_uses_new_weights(torch_cuda):
     n = sum(m.shape[0] for m in mats)
     for specs, f_in in (([LayerSpec(5, 32, 32)], 32), (reference_stack(K=1), 4), (reference_stack(K=3), 4)):
         net = ChebNet(specs, device="cuda:0")
-        net.set_weights(random_weights(specs, rng, 0.5))
+        ws0 = random_weights(specs, rng, 0.5)
+        ws0[-1] = (ws0[-1][0], np.abs(ws0[-1][1]) + 2.0)   # keep a final relu alive
+        net.set_weights(ws0)
         opt = KerasAdamReplay(net, learning_rate=5e-2)
         batch = GraphBatch.from_scipy(mats, device="cuda:0")
         X = rng.normal(size=(n, f_in))
