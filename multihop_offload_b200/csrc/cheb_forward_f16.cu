@@ -1324,7 +1324,7 @@ cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int 
     }
     const size_t smem = hf_smem_bytes(K, p.use_bits != 0, max_tile_nnz, &stage);
     p.stage_bytes = stage;
-    int grid = num_sms * (K <= 5 ? 2 : 1);
+    int grid = num_sms * (K <= 5 ? 2 : 1);   // (one CTA per SM per launch + more streams was measured: no gain)
     if (grid > p.b.n_tiles) grid = p.b.n_tiles;
     if (grid < 1) grid = 1;
     switch (K) {

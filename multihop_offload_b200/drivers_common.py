@@ -71,8 +71,28 @@ def sample_jobs(env, nodes_info, arrival_scale):
     return num_jobs
 
 
-def run_method(method, env, agent, apsp, explore=0.0):
-    """One of the methods of AdHoc_test.py:125-153 / AdHoc_train.py:124-157 -> (delay_emp, extras)."""
+def lookahead_instances(env, nodes_info, arrival_scale, n_instances, agent, apsp):
+    """job sets and GNN inputs of the next `n_instances` instances of a network WITHOUT disturbing the driver's
+    random stream: the generator state is saved, the instances are sampled exactly as the per-instance loop will sample
+    them (sample_jobs, then the draws each instance consumes before the next one: one np.random.uniform per job in each
+    of the two env.offloading() calls - baseline and GNN, offloading_v3.py:416 - whose VALUES are irrelevant at
+    explore = 0), their features are collected, the state is restored.  One GNN / head / shortest-path launch each
+    for all of them (ACOAgent.forward_instances)."""
+    state = np.random.get_state()
+    feats, obj0 = [], None
+    for _ in range(n_instances):
+        num_jobs = sample_jobs(env, nodes_info, arrival_scale)
+        obj = env.graph_expand()
+        obj0 = obj0 or obj
+        feats.append(agent.instance_features(obj))
+        np.random.uniform(0, 1, size=2 * num_jobs)
+    np.random.set_state(state)
+    return agent.forward_instances(obj0, env, feats, apsp)
+
+
+def run_method(method, env, agent, apsp, explore=0.0, pre=None):
+    """One of the methods of AdHoc_test.py:125-153 / AdHoc_train.py:124-157 -> (delay_emp, extras).
+    pre: precomputed (delay matrix, shortest paths) of this instance from lookahead_instances (method "GNN-pre")."""
     extras = {}
     if method == "baseline":
         dmtx_bl, dlist_bl, dproc_bl = env.dmtx_baseline()
@@ -103,6 +123,8 @@ def run_method(method, env, agent, apsp, explore=0.0):
     elif method == "GNN-test":
         obj = env.graph_expand()
         delay_links, delay_nodes, _ = agent.forward_env(obj, env)
+    elif method == "GNN-pre":
+        delay_links, delay_nodes, _ = agent.env_step_from(pre, env)
     else:
         raise ValueError(method)
     delay_emp = np.nansum(delay_links, axis=0) + np.nansum(delay_nodes, axis=0)

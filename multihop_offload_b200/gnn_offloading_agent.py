@@ -80,6 +80,8 @@ def _define():
     flags.DEFINE_string('modeldir', os.path.join('..', 'model'), 'directory holding model_ChebConv_* checkpoints.', **d)
     flags.DEFINE_integer('max_files', 0, 'process at most this many network files (0 = all).', **d)
     flags.DEFINE_integer('seed', -1, 'numpy/random seed of the drivers (-1 = unseeded like the reference).', **d)
+    flags.DEFINE_boolean('batch_instances', False, 'AdHoc_test: evaluate the 10 job instances of a network file in ONE GNN / queue-head / '
+                         'shortest-path launch each (same CSV rows as the per-instance loop under a fixed seed).', **d)
 
 
 _define()
@@ -305,6 +307,86 @@ class ACOAgent:
 
     def _on_gpu(self):
         return str(self.device).startswith("cuda") and hasattr(self.net, "ctx")
+
+    # ---- the instances of ONE network file in one launch each -------------------------
+    @staticmethod
+    def instance_features(obj):
+        """The four feature columns of :218-226 for one job instance (only column 2 differs between instances)."""
+        X = np.zeros((obj.num_edges_ext, 4))
+        X[:, 0] = obj.edge_self_loop
+        X[:, 1] = obj.edge_rate_ext
+        X[:, 2] = obj.jobs_arrivals
+        X[:, 3] = obj.edge_as_server
+        return X
+
+    def forward_instances(self, obj, env, feature_list, cpu_apsp=None):
+        """forward() + the shortest-path matrices of forward_env() (:278-287) for B job instances of one network: ONE
+        mho_cheb_forward launch over B copies of the extended line graph, ONE fused queue-head launch, ONE mho_apsp
+        launch.  obj / env: any instance of the network (topology, rates and maps are instance-invariant,
+        offloading_v3.py:262-339).  Returns a list of (delay_mtx_np, sp_gnn, sp_hop), one per instance - what
+        env_step_from() consumes."""
+        import networkx as nx
+        import torch
+        B = len(feature_list)
+        nn = obj.num_edges_ext
+        A = sp.csr_matrix(nx.adjacency_matrix(obj.gi_ext))
+        if not self._on_gpu():
+            # host stand-in (tests): the same quantities instance by instance through forward()'s own code path
+            out = []
+            hi = qh.HeadInputs(obj, env, self.device)
+            for X in feature_list:
+                lam64 = self.act(self.makestate(A, X)).detach().to(torch.float64)
+                ld, nd = qh.queue_delays(lam64[hi.maps_ol_el], lam64[hi.maps_on_el], hi.link_rates, hi.cf_degs, hi.node_mu, hi.adj_i, hi.T)
+                _, D_np = qh.delay_matrices(ld, nd, hi, self.bug_compatible)
+                for (src, dst) in env.graph_c.edges:
+                    env.graph_c[src][dst]["delay"] = D_np[src, dst]
+                out.append((D_np, cpu_apsp(env.graph_c, weight="delay"), cpu_apsp(env.graph_c, weight=None)))
+            return out
+        key = ("inst", B, A.shape[0], A.nnz, hash(A.indptr.tobytes()), hash(A.indices.tobytes()), hash(A.data.tobytes()))
+        batch = self._adj_cache.get(key)
+        if batch is None:
+            if len(self._adj_cache) > 64:
+                self._adj_cache.clear()
+            batch = GraphBatch.from_scipy([A] * B, device=self.device)
+            self._adj_cache[key] = batch
+        X = torch.as_tensor(np.ascontiguousarray(np.concatenate(feature_list, axis=0), dtype=np.float32), device=self.device)
+        lam = self.net.forward(batch, X)                                   # [B * nn, 1]
+        hi = qh.HeadInputs(obj, env, None)
+        adj_i = sp.csr_matrix(hi.adj_i_host)
+        hkey = ("inst", B, hi.link_rates_host.tobytes(), hi.node_mu_host.tobytes(), hi.maps_ol_el_host.tobytes(), hi.maps_on_el_host.tobytes(),
+                hi.cf_degs_host.tobytes(), adj_i.indptr.tobytes(), adj_i.indices.tobytes(), float(hi.T), int(nn))
+        hb = self._head_cache.get(hkey)
+        if hb is None:
+            if len(self._head_cache) > 32:
+                self._head_cache.clear()
+            hb = qh.HeadBatch([hi] * B, [nn] * B, self.net.ctx, self.device)
+            self._head_cache[hkey] = hb
+        ld, nd = hb.forward(lam, save=False)
+        L, nc = hi.num_links, len(hi.comp_nodes)
+        from .apsp import ApspPlan
+        plan = env.__dict__.get("_mho_apsp_inst")
+        if plan is None or plan.n_graphs != B or plan.n_edges != env.graph_c.number_of_edges():
+            plan = ApspPlan([env.graph_c] * B, device=self.device, ctx=self.net.ctx)
+            plan.n_edges = env.graph_c.number_of_edges()
+            env.__dict__["_mho_apsp_inst"] = plan
+        mats = []
+        for i in range(B):
+            _, D_np = qh.delay_matrices(ld[i * L:(i + 1) * L].reshape(-1, 1), nd[i * nc:(i + 1) * nc].reshape(-1, 1), hi, self.bug_compatible)
+            mats.append(D_np)
+        sps = plan.lengths(plan.entry_weights(mats))
+        hop = self._shortest_paths(env, mats[0], cpu_apsp)[1]              # topology only: cached on the env
+        return [(mats[i], sps[i], hop.copy()) for i in range(B)]
+
+    @staticmethod
+    def env_step_from(pre, env):
+        """The environment half of forward_env() (:281-290) from a precomputed (delay_mtx_np, sp_gnn, sp_hop)."""
+        delay_mtx_np, sp_gnn, sp_hop = pre
+        for (src, dst) in env.graph_c.edges:
+            env.graph_c[src][dst]["delay"] = delay_mtx_np[src, dst]
+        sp_gnn = np.array(sp_gnn, copy=True)
+        np.fill_diagonal(sp_gnn, np.diagonal(delay_mtx_np))
+        env.offloading(sp_gnn, sp_hop)
+        return env.run()
 
     def _shortest_paths(self, env, delay_mtx_np, cpu_apsp):
         """sp_gnn / sp_hop of :286-287.  On a CUDA device: mho_apsp (bit-identical to the reference's Dijkstra); the CSR

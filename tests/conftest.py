@@ -26,3 +26,13 @@ def built_lib():
     """libmho.so built in-tree (nvcc cross-compiles without a GPU)."""
     from multihop_offload_b200 import build
     return build.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`slow` tests (minutes of CPU) run only when asked for: `-m slow` or MHO_SLOW=1."""
+    if "slow" in (config.getoption("-m") or "") or os.environ.get("MHO_SLOW"):
+        return
+    skip = pytest.mark.skip(reason="slow: run with -m slow or MHO_SLOW=1")
+    for it in items:
+        if "slow" in it.keywords:
+            it.add_marker(skip)

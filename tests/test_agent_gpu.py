@@ -168,3 +168,30 @@ def test_shortest_path_matrices_on_device_equal_dijkstra(agent, golden_dir):
     plan = env.__dict__["_mho_apsp"]
     agent._shortest_paths(env, D_np, None)
     assert env.__dict__["_mho_apsp"] is plan
+
+
+def test_forward_instances_equals_per_instance_launches(agent, golden_dir):
+    """ten job instances of one network (same extended line graph, only the arrival column differs) through ONE
+    GNN launch + ONE queue-head launch + ONE shortest-path launch give, instance by instance, exactly what ten forward()
+    calls + ten APSP launches give (K = 1: per-node MLP; bit-identical)."""
+    for f in sorted(glob.glob(os.path.join(golden_dir, "case*.npz")))[:3]:
+        z = np.load(f)
+        obj, env = stub_case(z)
+        rng = np.random.default_rng(5)
+        feats, single = [], []
+        for i in range(10):
+            o = types.SimpleNamespace(**vars(obj))
+            o.jobs_arrivals = obj.jobs_arrivals * rng.uniform(0.0, 2.0, size=obj.jobs_arrivals.shape)
+            feats.append(agent.instance_features(o))
+            _, _, D_np = agent.forward(o, env)
+            sp_gnn, sp_hop = agent._shortest_paths(env, D_np, None)
+            single.append((D_np, sp_gnn, sp_hop))
+        l0 = agent.net.ctx.launch_count()
+        pre = agent.forward_instances(obj, env, feats, None)
+        launches = agent.net.ctx.launch_count() - l0
+        assert launches <= 4, launches      # GNN forward, queue head, weighted APSP (+ hop counts when not cached)
+        for (D1, s1, h1), (D2, s2, h2) in zip(single, pre):
+            assert np.array_equal(np.isnan(D1), np.isnan(D2))
+            m = ~np.isnan(D1)
+            assert np.array_equal(D1[m], D2[m])
+            assert np.array_equal(s1, s2) and np.array_equal(h1, h2)
