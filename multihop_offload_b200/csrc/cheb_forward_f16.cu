@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                    mask_a = smem_u32(mask_s), op_a = smem_u32(op_s);
     // control block: full[2] +0, empty[2] +16, parts +32, mma +40, tmem slot +48, tile info +64 ([buf][4]), reductions +96 ([3][2]),
     // running maxima +128 ([3][16]), row scales +512 ([2][128] floats)
-    const uint32_t bar_full = ctl_a, bar_empty = ctl_a + 16, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
+    const uint32_t bar_full = ctl_a, bar_empty = ctl_a + 16, bar_w = ctl_a + 32, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
     volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);
     unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
     unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);
@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         mbar_init(bar_empty, 8);
         mbar_init(bar_empty + 8, 8);
         mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);      // the weight image (one bulk copy)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) {
@@ -322,11 +323,12 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     if (warp == 0) {
         __syncwarp();
         if (n_my > 0) issue_load(0);   // the first tile's loads fly during the rest of the set-up
+        if (lane == 0) {               // the weight image is first needed by the first X W group / the first scales: one bulk
+            mbar_expect_tx(bar_w, (uint32_t)W_BYTES);   // copy, waited for where it is used, not here
+            bulk_g2s(w_a, p.wimg, (uint32_t)W_BYTES, bar_w);
+        }
         tmem_alloc(tslot, TCOLS);
     }
-    for (int c = tid; c < W_BYTES / 16; c += HF_COMPUTE_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
-    cp_async_commit();
-    cp_async_wait<0>();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -343,7 +345,6 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         const uint32_t key = r & 7u;
         const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
         const float* hdr_s = bias_s + 32;
-        const float inv_sw = hdr_s[0];
         const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
         uint32_t ph_mma = 0;
         float b1[16], b2[16];
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                 // dedicated issuer warp, costs 150-200)
                 bar_compute();
                 if (tid == 0) {
+                    mbar_wait(bar_w, 0u);   // (returns at once from the second tile on)
                     tc_fence_after();
                     // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh, two 16-wide K steps each
                     PROBE_M(11);
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
             // the tile's maxima are complete: every warp split this tile's rows before it arrived for a later group of the
             // previous tile, whose completion this thread has waited for (first tile: the barrier below)
-            if (j == 0) bar_compute();
+            if (j == 0) { bar_compute(); mbar_wait(bar_w, 0u); }   // (+ the weight image: header, bias)
             unsigned int* red = red_s + (j % 3) * 2;
             unsigned int* trk = track_s + (j % 3) * 16;
             float xmax = __uint_as_float(red[0]);
@@ -671,6 +673,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             PROBE_C(40);
             {
                 const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+                const float inv_sw = hdr_s[0];
                 const uint64_t W2 = pk2(inv_sw, inv_sw);
                 float y[16];
 #pragma unroll
@@ -731,497 +734,6 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// ---- ping-pong kernel: one CTA per SM, TWO tiles in flight -------------------------------------------------------------
-// The first kernel above keeps one tile per CTA and relies on the hardware interleaving two CTAs per SM; its clock marks
-// showed the two CTAs running in lockstep (both computing, then both waiting for the tensor pipe).  Here one CTA owns
-// both halves of tensor memory and its eight compute warps alternate between two tile slots in program order
-//      slot 0: split -> arrive      slot 1: split -> arrive      slot 0: wait, recurrence, split -> arrive   ...
-// so one slot's UMMAs always run under the other slot's CUDA-core work.  Each slot has its own control warp (loader +
-// UMMA issuer), part tile, staging buffers, mbarriers and 256 tensor-memory columns.  Further differences:
-//   * X is scaled PER ROW (the M dimension of X W): the row maximum is a 4-lane shuffle, no CTA barrier before the split;
-//     the tile maximum the Clenshaw scales need is collected with shared-memory atomics and read after the X W group,
-//     whose completion implies every warp's arrive;
-//   * 16-entry (conflict-free) lookup table for the adjacency expansion;
-//   * the first tile's loads are issued before the set-up barrier; output rows go out per lane quadrant (64-thread barrier).
-constexpr int PP_THREADS = 320;   // 8 compute warps + one control warp per slot
-
-template <int K, bool TRACK>
-__global__ void __launch_bounds__(PP_THREADS, 1) cheb_f16pp_kernel(const __grid_constant__ HfParams p) {
-    static_assert(K >= 2 && K <= 5, "two slots of 256 tensor-memory columns");
-    extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int W_BYTES = hf_w_bytes(K);
-    constexpr uint32_t ADJ_COL = 192u;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#ifdef MHO_PROBE
-    __shared__ long long probe_s[192];
-    const bool probe_on = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1;
-    int pn_c = 0, pn_m = 0;
-    if (tid < 192) probe_s[tid] = 0;
-    __syncthreads();
-    unsigned long long gt0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-#endif
-    PROBE_C(1);
-
-    // ---- shared memory carve-up: [slot 0: parts, 2 staging tiles][slot 1: same][weights][control block][LUT][masks][operator staging]
-    constexpr uint32_t SLOT_BYTES = 3u * HF_TILE_BYTES;
-    unsigned char* w_s = smem + 2 * SLOT_BYTES;
-    unsigned char* ctl_s = w_s + W_BYTES;           // 1536 B
-    unsigned char* lut_s = ctl_s + 1536;            // 16 x 8 B
-    unsigned char* mask_s = lut_s + 128;            // 2 x 2 KB bit rows built from a CSR slice
-    unsigned char* op_s = mask_s + 4096;            // 2 slots x 2 operator staging sets
-    const uint32_t smem_a = smem_u32(smem), w_a = smem_u32(w_s), ctl_a = smem_u32(ctl_s), lut_a = smem_u32(lut_s), mask_a = smem_u32(mask_s),
-                   op_a = smem_u32(op_s);
-    // control block: slot s at ctl + 64 s: full[2] +0, empty[2] +16, parts +32, mma +40; tmem slot +128; tile info +144 ([slot][buf][4]);
-    // reductions +208 ([slot][parity][2]); running maxima +256 ([slot][parity][16]); row scales +512 ([slot][128] floats)
-    volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 144);
-    unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 208);
-    unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 256);
-    float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
-
-    const int G = (int)gridDim.x;
-    const int n_my = (int)blockIdx.x < p.b.n_tiles ? (p.b.n_tiles - (int)blockIdx.x + G - 1) / G : 0;   // tiles of this CTA
-    const int n_slot[2] = {(n_my + 1) >> 1, n_my >> 1};                                                  // local tile j = 2 i + slot
-
-    // tile i of slot s -> staging buffer i & 1
-    auto issue_load = [&](int s, int i) {
-        const int buf = i & 1;
-        const int4 ti = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + (2 * i + s) * G));
-        const uint32_t fb = ctl_a + 64u * s + 8u * buf;
-        const uint32_t opb = op_a + (uint32_t)((2 * s + buf) * p.stage_bytes);
-        if (lane == 0) {
-            volatile int* t4 = tinfo_s + (s * 2 + buf) * 4;
-            t4[0] = ti.x; t4[1] = ti.y; t4[2] = ti.z; t4[3] = ti.w;
-            const uint32_t xb = (uint32_t)ti.y * 128u;
-            mbar_expect_tx(fb, xb + (p.use_bits ? (uint32_t)ti.y * 16u : 0u));
-            bulk_g2s(smem_a + (uint32_t)s * SLOT_BYTES + (uint32_t)(1 + buf) * HF_TILE_BYTES, p.X + (size_t)ti.x * 32, xb, fb);
-            if (p.use_bits) bulk_g2s(opb, p.b.adj_bits + (size_t)ti.x * 4, (uint32_t)ti.y * 16u, fb);
-        }
-        if (!p.use_bits) {
-            for (int e = lane; e <= ti.y; e += 32) cp_async4(opb + (uint32_t)e * 4u, p.b.rowptr + ti.x + e);
-            for (int e = lane; e < ti.w; e += 32) cp_async4(opb + 528u + (uint32_t)e * 4u, p.b.colidx + ti.z + e);
-            cp_async_mbar_arrive(fb);
-        }
-    };
-
-    if (warp >= 8) {
-        // control warp of slot (warp - 8): barriers, then the first tile's loads - before the set-up barrier
-        const int s = warp - 8;
-        if (lane == 0) {
-            const uint32_t cb = ctl_a + 64u * s;
-            const uint32_t full_count = p.use_bits ? 1u : 33u;
-            mbar_init(cb, full_count);
-            mbar_init(cb + 8, full_count);
-            mbar_init(cb + 16, 8);
-            mbar_init(cb + 24, 8);
-            mbar_init(cb + 32, 8);
-            mbar_init(cb + 40, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (n_slot[s] > 0) issue_load(s, 0);
-        if (s == 0) tmem_alloc(ctl_a + 128, 512u);
-    } else {
-        if (tid < 16) {
-            const uint32_t x = ((tid & 1) ? 0x3C00u : 0u) | ((tid & 2) ? 0x3C000000u : 0u), y = ((tid & 4) ? 0x3C00u : 0u) | ((tid & 8) ? 0x3C000000u : 0u);
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(lut_a + (uint32_t)tid * 8u), "r"(x), "r"(y) : "memory");
-        }
-        if (tid < 76) reinterpret_cast<unsigned int*>(ctl_s + 208)[tid] = 0u;   // reductions and running maxima
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int c = tid; c < W_BYTES / 16; c += HF_COMPUTE_THREADS) cp_async16(w_a + (uint32_t)c * 16u, p.wimg + (size_t)c * 16);
-        cp_async_commit();
-        cp_async_wait<0>();
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(ctl_s + 128);
-    PROBE_C(2);
-    PROBE_M(2);
-
-    if (warp >= 8) {
-        // =========================== control warp of one slot: bulk copies + UMMA issue ===========================
-        const int s = warp - 8;
-        const uint32_t cb = ctl_a + 64u * s, bar_parts = cb + 32, bar_mma = cb + 40;
-        const uint32_t parts_a = smem_a + (uint32_t)s * SLOT_BYTES;
-        const uint32_t tm = tmem_base + 256u * s;
-        uint32_t ph_parts = 0;
-        const int nt = n_slot[s];
-        for (int i = 0; i < nt; ++i) {
-            if (i + 1 < nt) {
-                if (i + 1 >= 2) {   // tile i - 1 of this slot (same buffer) has stored its output rows
-                    if (lane == 0) mbar_wait(cb + 16u + 8u * ((i + 1) & 1), (uint32_t)((((i + 1) >> 1) + 1) & 1));
-                    __syncwarp();
-                }
-                issue_load(s, i + 1);
-            }
-            if (lane == 0) {
-                PROBE_M(10);
-                mbar_wait(bar_parts, ph_parts);
-                ph_parts ^= 1u;
-                tc_fence_after();
-                PROBE_M(11);
-                {   // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh
-                    const uint32_t id_pos = idesc_f16((uint32_t)(32 * K), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * K), 0u, 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tm, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(w_a + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tm, desc_sw128(parts_a + 32u * ks), desc_sw128(w_a + 64u + 32u * ks), id_neg, 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tm, desc_sw128(parts_a + 32u * ks), desc_sw128(w_a + 32u * ks), id_pos, 1u);
-                }
-                umma_commit(bar_mma);
-                PROBE_M(12);
-                const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
-#pragma unroll 1
-                for (int k = K - 2; k >= 0; --k) {
-                    mbar_wait(bar_parts, ph_parts);
-                    ph_parts ^= 1u;
-                    tc_fence_after();
-                    PROBE_M(20 + k);
-                    const uint32_t d = tm + (uint32_t)(32 * (k + 1));
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, tm + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
-                    umma_commit(bar_mma);
-                    PROBE_M(30 + k);
-                }
-            }
-            __syncwarp();
-        }
-    } else {
-        // =========================== compute warps: two tile slots in program order ===========================
-        const int q = warp & 3, hh = warp >> 2;                 // TMEM lane quadrant, column half
-        const uint32_t r = (uint32_t)(q * 32 + lane);           // tile row = TMEM lane
-        const uint32_t key = r & 7u;
-        const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
-        const float* hdr_s = bias_s + 32;
-        const float inv_sw = hdr_s[0];
-        const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
-
-        struct Slot {
-            float b1[16], b2[16];
-            float inv_si;
-            int e_tau[K];     // clamped exponent fields of the bounds of |B_k|, k = 1 .. K-1
-            int rows, node0, nz0, buf;
-            uint32_t ph_mma;
-            float dmax2;
-        };
-        Slot st[2];
-        st[0].ph_mma = 0u; st[1].ph_mma = 0u;
-
-        // ---- phase X: input rows -> part tile (row-scaled), tile maxima via atomics, arrive
-        auto phase_x = [&](auto S_, int i) {
-            constexpr int S = decltype(S_)::value;
-            Slot& t = st[S];
-            const uint32_t cb = ctl_a + 64u * S;
-            const int buf = i & 1;
-            t.buf = buf;
-            PROBE_C(3);
-            mbar_wait(cb + 8u * buf, (uint32_t)((i >> 1) & 1));
-            PROBE_C(4);
-            volatile int* t4 = tinfo_s + (S * 2 + buf) * 4;
-            t.node0 = t4[0]; t.rows = t4[1]; t.nz0 = t4[2];
-            const int rows = t.rows;
-            const uint32_t parts_a = smem_a + (uint32_t)S * SLOT_BYTES;
-            const uint32_t xb_a = parts_a + (uint32_t)(1 + buf) * HF_TILE_BYTES;
-            const uint32_t opb = op_a + (uint32_t)((2 * S + buf) * p.stage_bytes);
-            float mx = 0.f;
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int cp = tid + 256 * pp, row = cp >> 2, q4 = cp & 3;
-                float x[8];
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (row < rows) { a = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
-                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-                float rm = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) rm = fmaxf(rm, fabsf(x[e]));
-                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 1));
-                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 2));   // the row's maximum (four lanes share a row)
-                mx = fmaxf(mx, rm);
-                int ex = expo_above(rm);                               // row max < 2^ex
-                ex = max(-100, min(110, ex));
-                const float s_row = pow2f(15 - ex);
-                if (q4 == 0) rowscale_s[S * 128 + row] = pow2f(ex - 15);
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split2(x[2 * e] * s_row, x[2 * e + 1] * s_row, h[e], l[e]);
-                const uint32_t ra = parts_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
-                sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
-                sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
-            }
-            // operator: max degree of the tile (and, from a CSR slice, the bit rows)
-            unsigned int deg = 0u;
-            if (p.use_bits) {
-                if (tid < rows) { const uint4 m4 = lds_u128(opb + (uint32_t)tid * 16u); deg = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w); }
-            } else {
-                const int row = tid >> 1, sub = tid & 1;
-                uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
-                if (row < rows) {
-                    const int e0 = (int)lds_u32(opb + (uint32_t)row * 4u) - t.nz0, e1 = (int)lds_u32(opb + (uint32_t)row * 4u + 4u) - t.nz0;
-                    deg = (unsigned int)(e1 - e0);
-                    for (int e = e0 + sub; e < e1; e += 2) {
-                        const uint32_t c = lds_u32(opb + 528u + (uint32_t)e * 4u) - (uint32_t)t.node0;
-                        const uint32_t bit = 1u << (c & 31u), w = c >> 5;
-                        m0 |= (w == 0u) ? bit : 0u;
-                        m1 |= (w == 1u) ? bit : 0u;
-                        m2 |= (w == 2u) ? bit : 0u;
-                        m3 |= (w == 3u) ? bit : 0u;
-                    }
-                }
-                m0 |= __shfl_xor_sync(0xffffffffu, m0, 1);
-                m1 |= __shfl_xor_sync(0xffffffffu, m1, 1);
-                m2 |= __shfl_xor_sync(0xffffffffu, m2, 1);
-                m3 |= __shfl_xor_sync(0xffffffffu, m3, 1);
-                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(mask_a + (uint32_t)S * 2048u + (uint32_t)row * 16u + (uint32_t)sub * 8u), "r"(sub ? m2 : m0), "r"(sub ? m3 : m1) : "memory");
-            }
-            {
-                const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
-                const unsigned int wd = __reduce_max_sync(0xffffffffu, deg);
-                unsigned int* red = red_s + (S * 2 + buf) * 2;
-                if (lane == 0) { atomicMax(red, wm); atomicMax(red + 1, wd); }
-            }
-            fence_proxy_async();
-            tc_fence_before();   // orders this thread's TMEM reads of the slot's previous tile before the next X W overwrites P
-            __syncwarp();
-            if (lane == 0) mbar_arrive(cb + 32);
-            PROBE_C(7);
-        };
-
-        // ---- phase A: the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), behind the X W group
-        auto phase_adj = [&](auto S_) {
-            constexpr int S = decltype(S_)::value;
-            Slot& t = st[S];
-            const uint32_t opb = op_a + (uint32_t)((2 * S + t.buf) * p.stage_bytes);
-            uint2 m2v = make_uint2(0u, 0u);
-            if ((int)r < t.rows) {
-                const uint32_t src = (p.use_bits ? opb : mask_a + (uint32_t)S * 2048u) + r * 16u + (uint32_t)hh * 8u;
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m2v.x), "=r"(m2v.y) : "r"(src));
-            }
-#pragma unroll
-            for (int w2 = 0; w2 < 2; ++w2) {
-                const uint32_t m = w2 ? m2v.y : m2v.x;
-                uint32_t aw[16];
-#pragma unroll
-                for (int b4 = 0; b4 < 8; ++b4) {
-                    uint2 v;
-                    const uint32_t idx = b4 == 0 ? ((m << 3) & 0x78u) : ((m >> (4 * b4 - 3)) & 0x78u);
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(lut_a + idx));
-                    aw[2 * b4] = v.x; aw[2 * b4 + 1] = v.y;
-                }
-                tmem_st16(tmem_base + 256u * S + ((uint32_t)(q * 32) << 16) + ADJ_COL + (uint32_t)(32 * hh + 16 * w2), aw);
-            }
-        };
-
-        // split B_k (b1) with tau_k into the slot's part tile and arrive
-        auto split_arrive = [&](auto S_, int e1) {
-            constexpr int S = decltype(S_)::value;
-            Slot& t = st[S];
-            const float tau = __uint_as_float((uint32_t)(269 - e1) << 23);
-            const uint32_t prow_a = smem_a + (uint32_t)S * SLOT_BYTES + r * 128u;
-            uint32_t h[8], l[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split2(t.b1[2 * e] * tau, t.b1[2 * e + 1] * tau, h[e], l[e]);
-            sts_u128(prow_a + (((uint32_t)(2 * hh) ^ key) << 4), h[0], h[1], h[2], h[3]);
-            sts_u128(prow_a + (((uint32_t)(2 * hh + 1) ^ key) << 4), h[4], h[5], h[6], h[7]);
-            sts_u128(prow_a + (((uint32_t)(4 + 2 * hh) ^ key) << 4), l[0], l[1], l[2], l[3]);
-            sts_u128(prow_a + (((uint32_t)(5 + 2 * hh) ^ key) << 4), l[4], l[5], l[6], l[7]);
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ctl_a + 64u * S + 32u);
-        };
-
-        // ---- phase I: X W done -> scales, B_K-1 = P_K-1, first split
-        auto phase_init = [&](auto S_) {
-            constexpr int S = decltype(S_)::value;
-            Slot& t = st[S];
-            const uint32_t tmem_row = tmem_base + 256u * S + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * hh);
-            PROBE_C(8);
-            mbar_wait(ctl_a + 64u * S + 40u, t.ph_mma);
-            t.ph_mma ^= 1u;
-            tc_fence_after();
-            PROBE_C(9);
-            // every warp has arrived for the X W group: the tile's maxima are complete
-            unsigned int* red = red_s + (S * 2 + t.buf) * 2;
-            const float xmax = __uint_as_float(red[0]);
-            t.dmax2 = 2.f * (float)red[1];
-            if (tid == 0) { unsigned int* o = red_s + (S * 2 + (t.buf ^ 1)) * 2; o[0] = 0u; o[1] = 0u; }
-            if (TRACK && tid < 16) track_s[(S * 2 + (t.buf ^ 1)) * 16 + tid] = 0u;
-            t.inv_si = rowscale_s[S * 128 + r];
-            {   // bounds of |B_k| (in units of the weight scale) -> exponent fields
-                float bet1 = 0.f, bet2 = 0.f;
-#pragma unroll
-                for (int k = K - 1; k >= 1; --k) {
-                    const float bet = xmax * hdr_s[1 + k] + t.dmax2 * bet1 + bet2;
-                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;   // bet < 2^(e - 127)
-                    t.e_tau[k] = max(30, min(240, e));
-                    bet2 = bet1;
-                    bet1 = bet;
-                }
-                t.e_tau[0] = 127;
-            }
-            uint32_t v[16];
-            tmem_ld16(tmem_row + (uint32_t)(32 * (K - 1)), v);
-            tmem_wait_ld_();
-            float m = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { t.b1[e] = __uint_as_float(v[e]) * t.inv_si; t.b2[e] = 0.f; if (TRACK) m = fmaxf(m, fabsf(t.b1[e])); }
-            if (TRACK) {
-                const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                if (lane == 0) atomicMax(track_s + (S * 2 + t.buf) * 16 + (K - 1), wm);
-            }
-            tmem_wait_st_();   // the adjacency stores have completed (first read by the first Clenshaw step's UMMAs)
-            split_arrive(S_, t.e_tau[K - 1]);
-            PROBE_C(20 + K - 2);
-        };
-
-        // ---- phase S_k: UMMAs of step k done -> B_k; k > 0: split and arrive; k = 0: epilogue
-        auto phase_step = [&](auto S_, auto K_) {
-            constexpr int S = decltype(S_)::value;
-            constexpr int k = decltype(K_)::value;
-            Slot& t = st[S];
-            const uint32_t tmem_row = tmem_base + 256u * S + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * hh);
-            // the UMMAs multiplied parts(B_k+1) scaled with tau_k+1
-            const int e1 = t.e_tau[k + 1];
-            unsigned int* trk = track_s + (S * 2 + t.buf) * 16;
-            mbar_wait(ctl_a + 64u * S + 40u, t.ph_mma);
-            t.ph_mma ^= 1u;
-            tc_fence_after();
-            PROBE_C(30 + k);
-            const float cfac = __uint_as_float((uint32_t)(e1 - 15 + (k > 0 ? 1 : 0)) << 23);   // (k > 0 ? 2 : 1) / tau_k+1
-            uint32_t vp[16], vh[16], vl[16];
-            tmem_ld16(tmem_row + (uint32_t)(32 * k), vp);
-            tmem_ld16(tmem_row + (uint32_t)(32 * (k + 1)), vh);
-            tmem_ld16(tmem_row + (uint32_t)(32 * (k + 2)), vl);
-            tmem_wait_ld_();
-            float m = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float bk = fmaf(__uint_as_float(vp[e]), t.inv_si, fmaf(__uint_as_float(vh[e]) - __uint_as_float(vl[e]), cfac, -t.b2[e]));
-                t.b2[e] = t.b1[e];
-                t.b1[e] = bk;
-                if (TRACK) m = fmaxf(m, fabsf(bk));
-            }
-            if (k > 0) {
-                if (TRACK) {
-                    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                    if (lane == 0) atomicMax(trk + k, wm);
-                }
-                int e0 = t.e_tau[k];
-                if (TRACK) {
-                    // the maxima of |B_k+1| and |B_k+2| are complete (their atomics preceded the arrive / UMMA / wait round of
-                    // this step): tighter bound of |B_k| than the a-priori one
-                    const float m1 = __uint_as_float(trk[k + 1]);
-                    const float m2 = (k + 2 <= K - 1) ? __uint_as_float(trk[k + 2]) : 0.f;
-                    const float bet = __uint_as_float(red_s[(S * 2 + t.buf) * 2]) * hdr_s[1 + k] + t.dmax2 * m1 + m2;
-                    e0 = max(30, min(240, (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1));
-                    t.e_tau[k] = e0;
-                }
-                split_arrive(S_, e0);
-                PROBE_C(20 + k - 1);
-            } else {
-                // epilogue: unscale, bias, activation; output rows through the staging tile as whole 128 B lines
-                PROBE_C(40);
-                const uint32_t xb_a = smem_a + (uint32_t)S * SLOT_BYTES + (uint32_t)(1 + t.buf) * HF_TILE_BYTES;
-                float y[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) y[e] = fmaf(t.b1[e], inv_sw, bias_s[16 * hh + e]);
-                if (p.act == MHO_ACT_RELU) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], 0.f);
-                } else if (leaky_max) {
-                    const float sl = p.slope;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], sl * y[e]);
-                } else if (p.act == MHO_ACT_LEAKY) {
-                    const float sl = p.slope;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) y[e] = y[e] > 0.f ? y[e] : sl * y[e];
-                }
-                const uint32_t ya = xb_a + r * 128u;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sts_f128(ya + (((uint32_t)(4 * hh + c) ^ key) << 4), make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]));
-                bar_quadrant(q);   // the two warps of this lane quadrant hold all 32 columns of its rows
-                float* dst = p.Y + (size_t)t.node0 * 32;
-#pragma unroll
-                for (int pp = 0; pp < 4; ++pp) {
-                    const uint32_t row = (uint32_t)(32 * q + 16 * hh + 4 * pp) + ((uint32_t)lane >> 3), ch = (uint32_t)lane & 7u;
-                    if ((int)row < t.rows) *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = lds_f128(xb_a + row * 128u + ((ch ^ (row & 7u)) << 4));
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ctl_a + 64u * S + 16u + 8u * (uint32_t)t.buf);   // the staging buffer may be refilled
-                PROBE_C(41);
-            }
-        };
-
-        using I0 = std::integral_constant<int, 0>;
-        using I1 = std::integral_constant<int, 1>;
-        const int n_pairs = (n_my + 1) >> 1;
-        for (int i = 0; i < n_pairs; ++i) {
-            const bool have1 = 2 * i + 1 < n_my;
-            phase_x(I0{}, i);
-            if (have1) phase_x(I1{}, i);
-            if (!p.use_bits) bar_compute();   // bit rows built from the CSR slices are read by other threads
-            phase_adj(I0{});
-            if (have1) phase_adj(I1{});
-            phase_init(I0{});
-            if (have1) phase_init(I1{});
-            if constexpr (K >= 5) { phase_step(I0{}, std::integral_constant<int, 3>{}); if (have1) phase_step(I1{}, std::integral_constant<int, 3>{}); }
-            if constexpr (K >= 4) { phase_step(I0{}, std::integral_constant<int, 2>{}); if (have1) phase_step(I1{}, std::integral_constant<int, 2>{}); }
-            if constexpr (K >= 3) { phase_step(I0{}, std::integral_constant<int, 1>{}); if (have1) phase_step(I1{}, std::integral_constant<int, 1>{}); }
-            phase_step(I0{}, std::integral_constant<int, 0>{});
-            if (have1) phase_step(I1{}, std::integral_constant<int, 0>{});
-        }
-    }
-
-    // ---- teardown
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512u);
-#ifdef MHO_PROBE
-    if (probe_on && tid == 0) {
-        unsigned long long gt1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
-        printf("cta %d tiles %d globaltimer start %llu end +%llu ns\n", (int)blockIdx.x, n_my, gt0, gt1 - gt0);
-        const long long base = probe_s[0] >> 8;
-        for (int i = 0; i < 192; ++i) {
-            if (probe_s[i] == 0) continue;
-            printf("cta %d %s id %2d  t %7lld\n", (int)blockIdx.x, i < 128 ? "C" : "M", (int)(probe_s[i] & 255), (probe_s[i] >> 8) - base);
-        }
-    }
-#endif
-}
-
-template <int K, bool TRACK>
-cudaError_t launch_pp(const HfParams& p, size_t smem, int grid, cudaStream_t st) {
-    static int smem_set[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if ((int)smem > smem_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(cheb_f16pp_kernel<K, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        smem_set[dev & 63] = (int)smem;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(PP_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    static int no_pdl = -1;
-    if (no_pdl < 0) { const char* e = getenv("MHO_NO_PDL"); no_pdl = e ? atoi(e) : 0; }
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, cheb_f16pp_kernel<K, TRACK>, p);
-}
-
 template <int K, bool TRACK>
 cudaError_t launch_k(const HfParams& p, size_t smem, int grid, cudaStream_t st) {
     static int smem_set[64] = {0};
@@ -1253,13 +765,6 @@ cudaError_t launch_k(const HfParams& p, size_t smem, int grid, cudaStream_t st) 
 // -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
-static size_t pp_smem_bytes(int K, bool has_bits, int max_tile_nnz, int* stage_bytes) {
-    const int nnz_cap = has_bits ? 0 : ((max_tile_nnz + 3) & ~3);
-    const int stage = has_bits ? 2048 : ((528 + nnz_cap * 4 + 15) & ~15);
-    if (stage_bytes) *stage_bytes = stage;
-    return (size_t)6 * HF_TILE_BYTES + (size_t)hf_w_bytes(K) + 1536 + 128 + 4096 + (size_t)4 * stage;
-}
-
 static size_t hf_smem_bytes(int K, bool has_bits, int max_tile_nnz, int* stage_bytes) {
     const int nnz_cap = has_bits ? 0 : ((max_tile_nnz + 3) & ~3);
     const int stage = has_bits ? 2048 : ((528 + nnz_cap * 4 + 15) & ~15);
@@ -1306,22 +811,9 @@ cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int 
     p.stagger = stagger_env;
     const int K = fp.layers[0].K;
     int stage = 0;
-    static int track_env = -1, v2_env = -1, pp_env = -1;
-    if (pp_env < 0) { const char* e = getenv("MHO_F16_PP"); pp_env = e ? atoi(e) : 0; }          // 1: experimental ping-pong variant (one CTA per SM)
+    static int track_env = -1;
     if (track_env < 0) { const char* e = getenv("MHO_TRACK"); track_env = e ? atoi(e) : 0; }   // 1: running-maximum scales for every K
-    if (v2_env < 0) { const char* e = getenv("MHO_F16_V2"); v2_env = e ? atoi(e) : 0; }         // 1: one tile per CTA, two CTAs per SM
     p.nnz_cap = p.use_bits ? 0 : ((max_tile_nnz + 3) & ~3);
-    if (K <= 5 && pp_env && !v2_env && pp_smem_bytes(K, p.use_bits != 0, max_tile_nnz, nullptr) <= (size_t)max_smem_optin) {
-        const size_t smem_pp = pp_smem_bytes(K, p.use_bits != 0, max_tile_nnz, &stage);
-        p.stage_bytes = stage;
-        int grid = std::min(num_sms, std::max(1, p.b.n_tiles));
-        switch (K) {
-            case 2: return track_env ? launch_pp<2, true>(p, smem_pp, grid, st) : launch_pp<2, false>(p, smem_pp, grid, st);
-            case 3: return track_env ? launch_pp<3, true>(p, smem_pp, grid, st) : launch_pp<3, false>(p, smem_pp, grid, st);
-            case 4: return track_env ? launch_pp<4, true>(p, smem_pp, grid, st) : launch_pp<4, false>(p, smem_pp, grid, st);
-            default: return track_env ? launch_pp<5, true>(p, smem_pp, grid, st) : launch_pp<5, false>(p, smem_pp, grid, st);
-        }
-    }
     const size_t smem = hf_smem_bytes(K, p.use_bits != 0, max_tile_nnz, &stage);
     p.stage_bytes = stage;
     int grid = num_sms * (K <= 5 ? 2 : 1);   // (one CTA per SM per launch + more streams was measured: no gain)
