@@ -194,15 +194,20 @@ __device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// number of graph-start marks in rows 1 .. row (128 flag bits): the index of the row's graph inside its tile
-__device__ __forceinline__ int group_of(const unsigned int* flags, int row) {
-    const uint4 f = *reinterpret_cast<const uint4*>(flags);
-    const int w = row >> 5;
-    const unsigned int below = (2u << (row & 31)) - 1u;   // bits 0 .. row & 31 (row & 31 == 31: all ones)
-    int g = __popc((w == 0 ? f.x : w == 1 ? f.y : w == 2 ? f.z : f.w) & below);
-    g += w > 0 ? __popc(f.x) : 0;
-    g += w > 1 ? __popc(f.y) : 0;
-    g += w > 2 ? __popc(f.z) : 0;
+// index of the graph of node `node` inside its tile: the number of graph starts <= node among the (sorted) node offsets of
+// the graphs that follow the tile's first one (`gb`: 128 staged entries; those beyond the tile are >= its end).  Tiles of
+// up to nine graphs take two 16 B loads; more graphs (tiny ones) walk on.
+__device__ __forceinline__ int group_of(uint32_t gb, int node, int node_end) {
+    const uint4 a = lds_u128(gb), b4 = lds_u128(gb + 16u);
+    int g = ((int)a.x <= node) + ((int)a.y <= node) + ((int)a.z <= node) + ((int)a.w <= node) + ((int)b4.x <= node) + ((int)b4.y <= node) +
+            ((int)b4.z <= node) + ((int)b4.w <= node);
+    if ((int)b4.w < node_end) {   // a ninth graph starts inside the tile
+        for (int e = 8; e < 128; ++e) {
+            const int bnd = (int)lds_u32(gb + (uint32_t)e * 4u);
+            if (bnd > node) break;
+            ++g;
+        }
+    }
     return g;
 }
 
@@ -254,7 +259,6 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     unsigned int* track_s = reinterpret_cast<unsigned int*>(ctl_s + 128);
     float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
     const uint32_t gb_a = smem_u32(grp_s);                                          // graph starts of the staged tiles
-    unsigned int* gflag_s = reinterpret_cast<unsigned int*>(grp_s + 1056);          // bit r set: a graph starts at tile row r
     unsigned int* gmax_s = reinterpret_cast<unsigned int*>(grp_s + 1056 + 64);      // max |x| (float bits) per graph of the tile
     unsigned int* gdeg_s = gmax_s + 3 * 128;                                        // max degree per graph of the tile
     const bool groups = p.b.tile_graph0 != nullptr;
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
         asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(lut_a + (uint32_t)tid * 8u), "r"(x), "r"(y) : "memory");
     }
     if (tid < 104) reinterpret_cast<unsigned int*>(ctl_s + 96)[tid] = 0u;   // reductions and running maxima
-    for (int i = tid; i < 16 + 6 * 128; i += HF_COMPUTE_THREADS) gflag_s[i] = 0u;   // graph-start flags, per-graph maxima
+    for (int i = tid; i < 6 * 128; i += HF_COMPUTE_THREADS) gmax_s[i] = 0u;   // per-graph maxima
     asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on global memory written by earlier launches in the stream is read
     if (warp == 0) {
         __syncwarp();
@@ -360,16 +364,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
             const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
             const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
-            unsigned int* gflag = gflag_s + (j % 3) * 4;
-            if (groups && part != 1) {
-                // mark the rows at which a graph starts (the flags were cleared a tile ago), then every thread counts the
-                // marks up to its row: the index of its graph inside the tile
-                if (tid < 128) {
-                    const int bnd = (int)lds_u32(gb_a + (uint32_t)(buf * 132 + tid) * 4u) - node0;
-                    if (bnd > 0 && bnd < rows) atomicOr(gflag + (bnd >> 5), 1u << (bnd & 31));
-                }
-                bar_compute();
-            }
+            const uint32_t gb = gb_a + (uint32_t)(buf * 132) * 4u;
             float mx = part == 1 ? mx_keep : 0.f;
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
@@ -388,8 +383,10 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                 const float s_row = pow2f(15 - ex);
                 if (q4 == 0) {
                     rowscale_s[buf * 128 + row] = pow2f(ex - 15);
-                    if (groups) atomicMax(gmax_s + (j % 3) * 128 + group_of(gflag, row), __float_as_uint(rm));
+                    
                 }
+                if (groups && q4 == 0 && row < rows)   // (a warp-level pre-reduction of these atomics was measured: no gain)
+                    atomicMax(gmax_s + (j % 3) * 128 + group_of(gb, node0 + row, node0 + rows), __float_as_uint(rm));
                 const uint64_t S2 = pk2(s_row, s_row);
                 uint32_t h[4], l[4];
 #pragma unroll
@@ -433,7 +430,7 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
                 const unsigned int wd = __reduce_max_sync(0xffffffffu, deg);
                 unsigned int* red = red_s + (j % 3) * 2;
                 if (lane == 0) { atomicMax(red, wm); atomicMax(red + 1, wd); }
-                if (groups && deg > 0u) atomicMax(gdeg_s + (j % 3) * 128 + group_of(gflag, p.use_bits ? tid : (tid >> 1)), deg);
+                if (groups && deg > 0u) atomicMax(gdeg_s + (j % 3) * 128 + group_of(gb, node0 + (p.use_bits ? tid : (tid >> 1)), node0 + rows), deg);
             }
             fence_proxy_async();   // the part tile is read by the tensor core
             PROBE_C(7);
@@ -557,14 +554,13 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
             const float xmax_tile = xmax, dmax2_tile = dmax2;
             (void)xmax_tile; (void)dmax2_tile;
             if (groups) {   // the graph of this thread's row: block-diagonal operator => its own scale per step
-                const int g = group_of(gflag_s + (j % 3) * 4, (int)r);
+                const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);   // (padding rows: the last graph)
                 xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
                 dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
             }
             if (tid == 0) { unsigned int* o = red_s + ((j + 2) % 3) * 2; o[0] = 0u; o[1] = 0u; }   // last read a tile ago, next written a tile ahead
             if (TRACK && tid < 16) track_s[((j + 2) % 3) * 16 + tid] = 0u;
             if (groups) {
-                if (tid < 4) gflag_s[((j + 2) % 3) * 4 + tid] = 0u;
                 if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
             }
             const float inv_si = rowscale_s[buf * 128 + r];
