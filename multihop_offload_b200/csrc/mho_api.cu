@@ -333,7 +333,7 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
     p.sched = c->sched;
     // one 32 -> 32 layer with 2 <= K <= 10 on a binary operator (the benchmark layer): second-generation tensor-core kernel
     if (b->tile_off && b->tile_info &&
-        cheb_f16_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, saved != nullptr, b->tile_graph0 != nullptr && b->graph_off != nullptr,
+        cheb_f16_eligible(layers, n_layers, b->vals != nullptr, b->adj_bits != nullptr, saved != nullptr && n_layers > 1 /* one layer keeps nothing */, b->tile_graph0 != nullptr && b->graph_off != nullptr,
                           b->max_tile_rows, b->max_tile_nnz, X, Y, b->adj_bits, c->max_smem_optin)) {
         rc = ensure_prepared_f16(c, layers[0], p.layers[0], (cudaStream_t)stream);
         if (rc) return rc;
@@ -510,10 +510,15 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     // uploads may start as soon as the slot is free (checked above): they do NOT wait for the caller's stream, whose
     // pending work is the other slot's kernels
     (void)ev_start;
-    CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
     if (d_go) {
-        CUDA_TRY(cudaMemcpyAsync(d_go, goff_h, b_go, cudaMemcpyHostToDevice, sh));
-        CUDA_TRY(cudaMemcpyAsync(d_tg, tgraph0.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, sh));
+        // tile descriptors, graph offsets and first-graph indices are adjacent on the device: ONE staged (pageable) copy
+        std::vector<int32_t> meta((al(b_ti) + al(b_go) + al(b_tg)) / 4, 0);
+        memcpy(meta.data(), tinfo.data(), (size_t)n_tiles * 16);
+        memcpy(meta.data() + al(b_ti) / 4, goff_h, b_go);
+        memcpy(meta.data() + (al(b_ti) + al(b_go)) / 4, tgraph0.data(), (size_t)n_tiles * 4);
+        CUDA_TRY(cudaMemcpyAsync(d_ti, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(d_ti, tinfo.data(), (size_t)n_tiles * 16, cudaMemcpyHostToDevice, sh));  // pageable: returns after staging
     }
 
     // node / nnz extent of each chunk (tiles of a chunk are a contiguous run of graphs)
