@@ -74,6 +74,7 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     if (c->wprep) cudaFree(c->wprep);
     if (c->wdense) cudaFree(c->wdense);
     if (c->wf16) cudaFree(c->wf16);
+    if (c->wmlp) cudaFree(c->wmlp);
     if (c->sched) cudaFree(c->sched);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
@@ -109,7 +110,7 @@ extern "C" int mho_host_free(void* ptr) {
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
 
 extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
-    if (c) { c->wprep_valid = false; c->wdense_valid = false; c->wf16_valid = false; }
+    if (c) { c->wprep_valid = false; c->wdense_valid = false; c->wf16_valid = false; c->wmlp_valid = false; }
     return MHO_OK;
 }
 
@@ -161,6 +162,29 @@ static int ensure_prepared_dense(mho_ctx* c, const mho_layer_t* layers, int n_la
     c->wdkey.clear();
     for (int l = 0; l < n_layers; ++l) c->wdkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
     c->wdense_valid = true;
+    return MHO_OK;
+}
+
+static int ensure_prepared_mlp(mho_ctx* c, const mho_layer_t* layers, int n_layers, const LayerDev* ld, cudaStream_t st) {
+    bool same = c->wmlp_valid && (int)c->wmkey.size() == n_layers;
+    for (int l = 0; same && l < n_layers; ++l) {
+        mho_wkey k{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out};
+        same = (k == c->wmkey[l]);
+    }
+    if (same) return MHO_OK;
+    const size_t bytes = (size_t)cheb_mlp_weight_bytes(n_layers);
+    if (bytes > c->wmlp_bytes) {
+        if (c->wmlp) CUDA_TRY(cudaFree(c->wmlp));
+        c->wmlp = nullptr; c->wmlp_bytes = 0;
+        if (cudaMalloc((void**)&c->wmlp, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
+        c->wmlp_bytes = bytes;
+    }
+    cudaError_t e = prepare_mlp_weights_launch(ld, n_layers, c->wmlp, st);
+    if (e != cudaSuccess) { mho_set_error("prepare_mlp_weights launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+    c->launches += 1;
+    c->wmkey.clear();
+    for (int l = 0; l < n_layers; ++l) c->wmkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
+    c->wmlp_valid = true;
     return MHO_OK;
 }
 
@@ -341,6 +365,15 @@ extern "C" int mho_cheb_forward(mho_ctx_t* c, const mho_batch_t* b, const mho_la
         cudaError_t e = cheb_f16_launch(p, c->wf16, b->max_tile_nnz, c->num_sms, c->max_smem_optin, (cudaStream_t)stream);
         dbg_check("f16 launched");
         if (e != cudaSuccess) { mho_set_error("cheb_f16 launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+        c->launches += 1;
+        return MHO_OK;
+    }
+    // stacks whose layers all have K = 1 (the model the reference ships): fused per-row MLP kernel, fp16 parts
+    if (b->tile_off && b->tile_info && cheb_mlp_eligible(layers, n_layers, b->max_tile_rows, X, c->max_smem_optin)) {
+        rc = ensure_prepared_mlp(c, layers, n_layers, p.layers, (cudaStream_t)stream);
+        if (rc) return rc;
+        cudaError_t e = cheb_mlp_launch(p, c->wmlp, c->num_sms, (cudaStream_t)stream);
+        if (e != cudaSuccess) { mho_set_error("cheb_mlp launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
         c->launches += 1;
         return MHO_OK;
     }

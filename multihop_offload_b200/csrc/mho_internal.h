@@ -43,6 +43,11 @@ struct mho_ctx {
     bool wf16_valid = false;
     unsigned char* wf16 = nullptr;
     size_t wf16_bytes = 0;
+    // fp16 weight images of the fused K = 1 stack kernel (cheb_mlp_f16.cu)
+    std::vector<mho_wkey> wmkey;
+    bool wmlp_valid = false;
+    unsigned char* wmlp = nullptr;
+    size_t wmlp_bytes = 0;
     int* sched = nullptr;  // two zero-initialised ints: dynamic tile scheduler state (self re-arming)
     int device = 0;
     int num_sms = 0;
@@ -71,6 +76,10 @@ bool cheb_f16_eligible(const mho_layer_t* layers, int n_layers, bool has_vals, b
 int cheb_f16_weight_bytes(int K);
 cudaError_t prepare_f16_weights_launch(const LayerDev& L, unsigned char* out, cudaStream_t st);
 cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int max_tile_nnz, int num_sms, int max_smem_optin, cudaStream_t st);
+bool cheb_mlp_eligible(const mho_layer_t* layers, int n_layers, int max_tile_rows, const void* X, int max_smem_optin);
+int cheb_mlp_weight_bytes(int n_layers);
+cudaError_t prepare_mlp_weights_launch(const LayerDev* layers, int n_layers, unsigned char* out, cudaStream_t st);
+cudaError_t cheb_mlp_launch(const FwdParams& fp, const unsigned char* wimg, int num_sms, cudaStream_t st);
 cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
                         const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
