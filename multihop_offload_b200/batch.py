@@ -170,6 +170,26 @@ class GraphBatch:
             self.dev["rowptr_t"], self.dev["colidx_t"], self.dev["vals_t"] = (up(a) for a in self.transpose)
         return self
 
+    def _graph_bits(self):
+        """Bit rows relative to each GRAPH's first node (the tensor-core VJP runs one graph per CTA pass); built and
+        uploaded on first use.  None for weighted operators or graphs of more than 128 nodes."""
+        if "adj_bits_graph" in self.dev:
+            return self.dev["adj_bits_graph"]
+        import torch
+        t = None
+        if self.vals is None and self.n_graphs and self.total_nodes and self.max_graph_rows <= 128:
+            if self.adj_bits is not None and self.n_tiles == self.n_graphs:
+                t = self.dev["adj_bits"]   # every tile is one graph
+            else:
+                bits = np.zeros((self.total_nodes, 4), dtype=np.uint32)
+                one_per_tile = np.arange(self.n_graphs + 1, dtype=np.int32)
+                _lib.check(_lib.load_library().mho_fill_adj_bits(
+                    self.graph_off.ctypes.data, self.rowptr.ctypes.data, self.colidx.ctypes.data if self.total_nnz else None,
+                    one_per_tile.ctypes.data, self.n_graphs, bits.ctypes.data), "mho_fill_adj_bits")
+                t = torch.from_numpy(bits.view(np.int32)).to(self.device)
+        self.dev["adj_bits_graph"] = t
+        return t
+
     def struct_ref(self, per_graph_tiles=False, row_tiles=False):
         """Cached ctypes byref of the mho_batch_t (device arrays never move after .to())."""
         key = (bool(per_graph_tiles), bool(row_tiles))
@@ -202,6 +222,8 @@ class GraphBatch:
             b.tile_off, b.n_tiles = None, self.n_graphs
             b.tile_info = self.dev["graph_info"].data_ptr()
             b.max_tile_rows, b.max_tile_nnz = self.max_graph_rows, self.max_graph_nnz
+            gb = self._graph_bits()
+            b.adj_bits = gb.data_ptr() if gb is not None else None
         else:
             b.tile_off, b.n_tiles = self.dev["tile_off"].data_ptr(), self.n_tiles
             b.tile_info = self.dev["tile_info"].data_ptr()

@@ -332,6 +332,12 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     if ((b->rowptr_t == nullptr) != (b->colidx_t == nullptr)) { mho_set_error("mho_cheb_backward: rowptr_t/colidx_t must both be set or both NULL"); return MHO_ERR_INVALID; }
     if (b->max_tile_rows < 1) { mho_set_error("mho_cheb_backward: batch.max_tile_rows must be the largest graph"); return MHO_ERR_INVALID; }
 
+    const bool use_f16 = cheb_backward_f16_eligible(b, layers, n_layers, X, Y, dY, dX, c->max_smem_optin);
+    if (use_f16) {
+        cudaError_t e = cheb_backward_f16_launch(b, layers, X, Y, dY, grads_per_graph, (long long)P, c->num_sms, st);
+        if (e != cudaSuccess) { mho_set_error("cheb_backward_f16 launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+        c->launches += 1;
+    }
     BwdParams p;
     memset(&p, 0, sizeof(p));
     p.b.graph_off = b->graph_off; p.b.rowptr = b->rowptr; p.b.colidx = b->colidx; p.b.vals = b->vals;
@@ -367,11 +373,12 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     if (per_sm > 4) per_sm = 4;   // 56-64 registers x 256 threads: four CTAs fit the register file
     int grid = c->num_sms * per_sm;
     if (grid > b->n_graphs) grid = b->n_graphs;
-    cudaError_t e;
-    if (has_vals) e = staged ? launch_bwd<true, true>(p, grid, smem, st) : launch_bwd<true, false>(p, grid, smem, st);
+    cudaError_t e = cudaSuccess;
+    if (use_f16) { /* done above */ }
+    else if (has_vals) e = staged ? launch_bwd<true, true>(p, grid, smem, st) : launch_bwd<true, false>(p, grid, smem, st);
     else e = staged ? launch_bwd<false, true>(p, grid, smem, st) : launch_bwd<false, false>(p, grid, smem, st);
     if (e != cudaSuccess) { mho_set_error("cheb_backward launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
-    c->launches += 1;
+    if (!use_f16) c->launches += 1;
     if (grads_sum) {
         const int threads = 128;
         float* part = (float*)mho_scratch(c, 1, (size_t)MHO_SUM_SLICES * P * sizeof(float));

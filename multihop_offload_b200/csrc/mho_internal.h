@@ -80,6 +80,10 @@ bool cheb_mlp_eligible(const mho_layer_t* layers, int n_layers, int max_tile_row
 int cheb_mlp_weight_bytes(int n_layers);
 cudaError_t prepare_mlp_weights_launch(const LayerDev* layers, int n_layers, unsigned char* out, cudaStream_t st);
 cudaError_t cheb_mlp_launch(const FwdParams& fp, const unsigned char* wimg, int num_sms, cudaStream_t st);
+bool cheb_backward_f16_eligible(const mho_batch_t* b, const mho_layer_t* layers, int n_layers, const void* X, const void* Y, const void* dY,
+                                const void* dX, int max_smem_optin);
+cudaError_t cheb_backward_f16_launch(const mho_batch_t* b, const mho_layer_t* layers, const float* X, const float* Y, const float* dY,
+                                     float* grads, long long n_params, int num_sms, cudaStream_t st);
 cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
                         const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
