@@ -283,6 +283,52 @@ __global__ void grads_sum_stage2(const float* __restrict__ part, float* __restri
     out[p] = s;
 }
 
+// One-launch variant for parameter counts that are multiples of 4 (every 32-wide layer): float4 columns, 64 slices of
+// graphs summed with 8 loads in flight, and the LAST block of each column group (a self re-arming counter) adds the 64
+// slice sums in slice order - the result does not depend on which block that is.
+#define MHO_SUM_SLICES4 64
+__global__ void __launch_bounds__(128) grads_sum_fused(const float4* __restrict__ grads, float4* part, float4* __restrict__ out, unsigned int* counters,
+                                                        int n_graphs, int n_params4) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    const int per = (n_graphs + MHO_SUM_SLICES4 - 1) / MHO_SUM_SLICES4;
+    const int g0 = blockIdx.y * per, g1 = min(g0 + per, n_graphs);
+    if (col < n_params4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int g = g0;
+        for (; g + 8 <= g1; g += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldcs(grads + (size_t)(g + i) * n_params4 + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+        }
+        for (; g < g1; ++g) { const float4 v = __ldcs(grads + (size_t)g * n_params4 + col); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        __stcg(part + (size_t)blockIdx.y * n_params4 + col, s);
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ int last_s;
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counters + blockIdx.x, 1u);
+        last_s = (t == (unsigned int)(MHO_SUM_SLICES4 - 1));
+        if (last_s) counters[blockIdx.x] = 0u;   // re-armed for the next call (stream order)
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (col < n_params4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i0 = 0; i0 < MHO_SUM_SLICES4; i0 += 16) {
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __ldcg(part + (size_t)(i0 + i) * n_params4 + col);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+        }
+        out[col] = s;
+    }
+}
+
 static size_t bwd_smem_bytes(int rows_cap, int nnz_cap, int w_floats, bool has_vals) {
     size_t s = (size_t)rows_cap * 128 * 3 + (size_t)w_floats * 4;
     s += (size_t)((rows_cap + 1 + 3) & ~3) * 4;
@@ -381,14 +427,34 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     if (!use_f16) c->launches += 1;
     if (grads_sum) {
         const int threads = 128;
-        float* part = (float*)mho_scratch(c, 1, (size_t)MHO_SUM_SLICES * P * sizeof(float));
-        if (!part) { mho_set_error("mho_cheb_backward: cudaMalloc of the reduction scratch failed"); return MHO_ERR_CUDA; }
-        const dim3 g1((unsigned)((P + threads - 1) / threads), MHO_SUM_SLICES);
-        grads_sum_stage1<<<g1, threads, 0, st>>>(grads_per_graph, part, b->n_graphs, P);
-        grads_sum_stage2<<<g1.x, threads, 0, st>>>(part, grads_sum, P);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) { mho_set_error("grads_sum launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
-        c->launches += 2;
+        const bool vec4 = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(grads_per_graph) | reinterpret_cast<uintptr_t>(grads_sum)) & 15u) == 0;
+        if (vec4) {
+            const int P4 = (int)(P / 4);
+            const int nblk = (P4 + threads - 1) / threads;
+            // scratch: one counter per column group (4 KB at a fixed place: zeroed when the slot is (re)allocated, self re-arming
+            // after that), then the 64 slice sums
+            const size_t cnt_bytes = 4096;
+            if ((size_t)nblk * sizeof(unsigned int) > cnt_bytes) { mho_set_error("mho_cheb_backward: %lld parameters exceed the reduction's column groups", (long long)P); return MHO_ERR_TOO_LARGE; }
+            const size_t need = cnt_bytes + (size_t)MHO_SUM_SLICES4 * P * sizeof(float);
+            const bool fresh = c->scratch.size() <= 2 || c->scratch[2].bytes < need;
+            unsigned char* sc = (unsigned char*)mho_scratch(c, 2, need);
+            if (!sc) { mho_set_error("mho_cheb_backward: cudaMalloc of the reduction scratch failed"); return MHO_ERR_CUDA; }
+            if (fresh && cudaMemsetAsync(sc, 0, cnt_bytes, st) != cudaSuccess) { mho_set_error("mho_cheb_backward: memset failed"); return MHO_ERR_CUDA; }
+            grads_sum_fused<<<dim3((unsigned)nblk, MHO_SUM_SLICES4), threads, 0, st>>>((const float4*)grads_per_graph, (float4*)(sc + cnt_bytes), (float4*)grads_sum,
+                                                                                     (unsigned int*)sc, b->n_graphs, P4);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { mho_set_error("grads_sum launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+            c->launches += 1;
+        } else {
+            float* part = (float*)mho_scratch(c, 1, (size_t)MHO_SUM_SLICES * P * sizeof(float));
+            if (!part) { mho_set_error("mho_cheb_backward: cudaMalloc of the reduction scratch failed"); return MHO_ERR_CUDA; }
+            const dim3 g1((unsigned)((P + threads - 1) / threads), MHO_SUM_SLICES);
+            grads_sum_stage1<<<g1, threads, 0, st>>>(grads_per_graph, part, b->n_graphs, P);
+            grads_sum_stage2<<<g1.x, threads, 0, st>>>(part, grads_sum, P);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { mho_set_error("grads_sum launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+            c->launches += 2;
+        }
     }
     return MHO_OK;
 }
