@@ -12,7 +12,10 @@
  * all array arguments are caller-owned DEVICE pointers unless the name ends in _host; the
  * callee never frees caller memory; every launch goes to the caller-supplied stream; no hidden
  * synchronisation except in the *_host convenience calls (documented).  One context per
- * (thread, GPU).  fp32 storage, fp32 accumulate, 3xTF32 split products on the tensor cores.
+ * (thread, GPU) - and one per stream when several streams launch concurrently (a context holds
+ * reduction scratch and staging slots).  fp32 storage, fp32 accumulate; tensor-core operands are exact
+ * multi-part splits of the fp32 values (two fp16 parts after power-of-two scales, three bf16 parts,
+ * or TF32 hi/lo, depending on the kernel): results agree with an fp32 evaluation to round-off.
  */
 #ifndef MHO_H_
 #define MHO_H_
@@ -74,7 +77,8 @@ typedef struct {
     /* optional (device, 16 B aligned): the BINARY operator as bit rows, [total_nodes][4] words; bit j of word w of
        node i = "i is adjacent to node tile_node0(i) + 32 w + j" (tile of the plan above, <= 128 nodes, from
        mho_fill_adj_bits).  With it the forward's tensor-core path (vals == NULL, tiles <= 128 nodes) reads 16 B per
-       node instead of walking the CSR slice; NULL => the kernel derives the bits from rowptr/colidx itself. */
+       node instead of walking the CSR slice; NULL => the kernel derives the bits from rowptr/colidx itself.  In a batch
+       with tile_off == NULL (one tile per graph: mho_cheb_backward) the bits are relative to the graph's first node. */
     const uint32_t* adj_bits;
     /* optional (device), [n_tiles] parallel to tile_info: index of the FIRST graph of each listed tile (its graphs are
        consecutive).  With it the fp16-part tensor-core forward scales its operands per GRAPH (graph_off is then read on
@@ -104,7 +108,7 @@ int mho_version(void);
 /* number of kernels launched through this context so far (bench.py's gpu_launches claim) */
 int64_t mho_launch_count(const mho_ctx_t* ctx);
 
-/* The forward snapshots the weights of a layer set into packed TF32 hi/lo images the first time it sees
+/* The forward snapshots the weights of a layer set into packed operand images the first time it sees
  * a given set of (W, b) pointers and reuses them afterwards.  Call this after modifying weights IN PLACE
  * behind the library's back (mho_adam_replay does it itself). */
 int mho_invalidate_weights(mho_ctx_t* ctx);
@@ -129,11 +133,15 @@ int mho_fill_adj_bits(const int32_t* graph_off_host, const int32_t* rowptr_host,
  * (gnn_offloading_agent.py:144-150) for a whole batch.  X [total_nodes, layers[0].f_in],
  * Y [total_nodes, layers[n-1].f_out], both row-major fp32.  `saved` (nullable) receives the
  * inputs of layers 1..n-1 (the hidden activations) for the VJP: mho_saved_bytes() bytes.
- * Kernel selection (results agree to fp32 round-off): with tile_off + tile_info, tiles of <= 128 nodes, <= 32
- * features per layer, K <= 5 and either a binary operator (vals == NULL) or K = 1 everywhere, the all-tensor-core
- * kernel runs (tcgen05 / TMEM, csrc/cheb_forward_dense.cu); otherwise the CSR-walk kernel (csrc/cheb_forward.cu).
- * With K = 1 in every layer the operator is never read and tile_info may describe ANY runs of <= 128 consecutive nodes
- * (they need not respect graph boundaries).  With vals == NULL the CSR must not hold duplicate entries. */
+ * Kernel selection (results agree to fp32 round-off; all tcgen05 / TMEM kernels need tile_off + tile_info and tiles of
+ * <= 128 nodes):
+ *   - one layer 32 -> 32, 2 <= K <= 10, vals == NULL, tile_graph0 set: csrc/cheb_forward_f16.cu (fp16 two-part operands);
+ *   - every layer K = 1, <= 32 features (first f_in a multiple of 4): csrc/cheb_mlp_f16.cu, the whole stack in one launch;
+ *     the operator is never read and tile_info may describe ANY runs of <= 128 consecutive nodes (they need not respect
+ *     graph boundaries);
+ *   - <= 32 features per layer, K <= 5, vals == NULL: csrc/cheb_forward_dense.cu (bf16 three-part operands, fused stacks);
+ *   - everything else (weighted operators, tiles of up to 512 nodes, K up to 16): the CSR-walk kernel csrc/cheb_forward.cu.
+ * With vals == NULL the CSR must not hold duplicate entries. */
 int mho_cheb_forward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
                      int32_t n_layers, const float* X, float* Y, void* saved, mho_stream_t stream);
 size_t mho_saved_bytes(const mho_batch_t* batch, const mho_layer_t* layers, int32_t n_layers);
@@ -144,7 +152,10 @@ size_t mho_saved_bytes(const mho_batch_t* batch, const mho_layer_t* layers, int3
  * [n_graphs, n_params] receives one flat gradient per graph instance in variable-creation order
  * (kernel_0, bias_0, kernel_1, ...; the order the reference memorises them, :142,:450);
  * grads_sum [n_params] (nullable) their deterministic sum (the buffer a data-parallel
- * all-reduce ships).  dX nullable.  Requires a one-graph-per-tile batch (tile_off == NULL). */
+ * all-reduce ships).  dX nullable.  Requires a one-graph-per-tile batch (tile_off == NULL).
+ * One layer 32 -> 32, 2 <= K <= 10, vals == NULL, graphs of <= 128 nodes, dX == NULL and batch->adj_bits set (bit rows
+ * relative to each GRAPH's first node: what mho_fill_adj_bits gives for tile_off = 0, 1, 2, ...) runs on the tensor
+ * cores (csrc/cheb_backward_f16.cu); every other shape on csrc/cheb_backward.cu. */
 int mho_cheb_backward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
                       int32_t n_layers, const float* X, const float* Y, const void* saved,
                       const float* dY, float* grads_per_graph, float* grads_sum, float* dX,

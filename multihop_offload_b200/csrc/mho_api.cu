@@ -114,7 +114,7 @@ extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
     return MHO_OK;
 }
 
-// (Re)build the packed TF32 hi/lo weight images when the layer set or the weights changed.
+// (Re)build the packed TF32 hi/lo weight images of the CSR-walk kernel when the layer set or the weights changed.
 static int ensure_prepared(mho_ctx* c, const mho_layer_t* layers, int n_layers, const LayerDev* ld, cudaStream_t st) {
     bool same = c->wprep_valid && (int)c->wkey.size() == n_layers;
     for (int l = 0; same && l < n_layers; ++l) {

@@ -39,6 +39,7 @@ def timeit(fn, name):
 Y, saved = net.forward(b, X, save=True)
 timeit(lambda: net.forward(b, X, save=True), "forward(save)")
 timeit(lambda: net.backward(b, X, Y, saved, dY), "backward")
+timeit(lambda: net.backward(b, X, Y, saved, dY, need_sum=False), "backward (no sum)")
 def both():
     Yt, sv = net.forward(b, X, save=True); net.backward(b, X, Yt, sv, dY)
 timeit(both, "forward+backward")
