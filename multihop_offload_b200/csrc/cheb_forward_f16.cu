@@ -635,6 +635,510 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
     if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
+// ---- warp-specialised variant (K <= 5, bit rows, per-graph scales) ---------------------------------------------------------
+// Same arithmetic as cheb_f16_kernel - the two kernels give bit-identical results - with the work that does not belong to the
+// dependent chain of a tile moved off the eight compute warps (12 warps per CTA, two CTAs per SM, register budgets re-balanced
+// with setmaxnreg):
+//   * warps 0-7, COMPUTE (thread = one row x 16 columns): adjacency expansion under the X W group, then per round trip: wait,
+//     tensor-memory load, recurrence in packed fp32, split, arrive; the output rows go to the staging tile and are left there.
+//   * warps 8-10, SERVICE (96 threads): bulk loads two tiles ahead, the row split of the NEXT tile (per-row scales, per-graph
+//     maxima), the coalesced output store of the CURRENT tile.
+//   * warp 11, ISSUE: one thread issues every tcgen05.mma group (an issuing thread stalls until the tensor pipe has accepted the
+//     group: 50-130 cycles per UMMA with two CTAs sharing the pipe).
+// Hand-offs: named barriers with fixed arrive / sync counts where the two sides alternate strictly (parts ready: 256 + 32, output
+// rows staged: 256 + 96), monotonic shared-memory counters where one side may run ahead (rows split, part tile free).
+__device__ __forceinline__ void ws_parts_arrive() { asm volatile("bar.arrive 1, 288;" ::: "memory"); }
+__device__ __forceinline__ void ws_parts_wait() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
+__device__ __forceinline__ void ws_out_arrive() { asm volatile("bar.arrive 2, 352;" ::: "memory"); }
+__device__ __forceinline__ void ws_out_wait() { asm volatile("bar.sync 2, 352;" ::: "memory"); }
+__device__ __forceinline__ void ws_service_sync() { asm volatile("bar.sync 3, 96;" ::: "memory"); }
+__device__ __forceinline__ void ws_compute_sync() { asm volatile("bar.sync 4, 256;" ::: "memory"); }
+__device__ __forceinline__ void ws_poll(volatile int* c, int target) { while (*c < target) { } }
+__device__ __forceinline__ void tmem_ld8_(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constant__ HfParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int W_BYTES = hf_w_bytes(K);
+    constexpr uint32_t TCOLS = 256u, ADJ_COL = TCOLS - 64u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef MHO_PROBE
+    __shared__ long long wprobe_s[256];
+    int wpn = 0;
+    if (tid < 256) wprobe_s[tid] = 0;
+    __syncthreads();
+#define WPROBE(id) do { if (blockIdx.x == 0 && (tid == 0 || tid == 256 || tid == 352) && wpn < 80) { wprobe_s[(tid == 0 ? 0 : tid == 256 ? 88 : 176) + wpn] = (clock64() << 8) | (long long)(id); ++wpn; } } while (0)
+#else
+#define WPROBE(id) do { } while (0)
+#endif
+    // shared memory: as in cheb_f16_kernel (two part tiles | two staging tiles | weights | control block | LUT | masks (unused) |
+    // operator staging | graph starts and per-graph maxima)
+    unsigned char* w_s = smem + 4 * HF_TILE_BYTES;
+    unsigned char* ctl_s = w_s + W_BYTES;
+    unsigned char* lut_s = ctl_s + 1536;
+    unsigned char* op_s = lut_s + 128 + 4096;
+    unsigned char* grp_s = op_s + 2 * p.stage_bytes;
+    const uint32_t smem_a = smem_u32(smem), xs_a = smem_a + 2u * HF_TILE_BYTES, w_a = smem_u32(w_s), ctl_a = smem_u32(ctl_s), lut_a = smem_u32(lut_s),
+                   op_a = smem_u32(op_s);
+    // control block: full[2] +0, weights +32, mma +40, tmem slot +48, rows-split counter +56, part-tile-free counter +60, tile info +64
+    // ([buf][4]), reductions +96 ([3][2]), row scales +512 ([2][128] floats)
+    const uint32_t bar_full = ctl_a, bar_w = ctl_a + 32, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
+    volatile int* xs_count = reinterpret_cast<volatile int*>(ctl_s + 56);   // + 3 per tile whose rows are split (service warps)
+    volatile int* pf_count = reinterpret_cast<volatile int*>(ctl_s + 60);   // + 8 per tile whose UMMAs are all complete (compute warps)
+    volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);
+    unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
+    float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
+    const uint32_t gb_a = smem_u32(grp_s);
+    unsigned int* gmax_s = reinterpret_cast<unsigned int*>(grp_s + 1056 + 64);
+    unsigned int* gdeg_s = gmax_s + 3 * 128;
+
+    const int G = (int)gridDim.x;
+    const int n_my = (int)blockIdx.x < p.b.n_tiles ? (p.b.n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+
+    if (tid == 0) {
+        mbar_init(bar_full, 33u);        // expect_tx arrive + one cp.async arrive per lane of the loading warp
+        mbar_init(bar_full + 8, 33u);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        *xs_count = 3;
+        *pf_count = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 16) {
+        const uint32_t x = ((tid & 1) ? 0x3C00u : 0u) | ((tid & 2) ? 0x3C000000u : 0u), y = ((tid & 4) ? 0x3C00u : 0u) | ((tid & 8) ? 0x3C000000u : 0u);
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(lut_a + (uint32_t)tid * 8u), "r"(x), "r"(y) : "memory");
+    }
+    if (tid >= 32 && tid < 38) red_s[tid - 32] = 0u;
+    for (int i = tid; i < 6 * 128; i += 384) gmax_s[i] = 0u;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp == 0) tmem_alloc(tslot, TCOLS);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(ctl_s + 48);
+
+    if (warp < 8) {
+        // ======================================================= compute warps =======================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        const int q = warp & 3, hh = warp >> 2;
+        const uint32_t r = (uint32_t)(q * 32 + lane);
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * hh);
+        const uint32_t key = r & 7u;
+        const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
+        const float* hdr_s = bias_s + 32;
+        const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
+        uint32_t ph_mma = 0;
+        float b1[16], b2[16];
+        auto split_arrive = [&](int buf, int e1) {
+            const uint64_t T2 = pk2(__uint_as_float((uint32_t)(269 - e1) << 23), __uint_as_float((uint32_t)(269 - e1) << 23));
+            const uint32_t prow_a = smem_a + (uint32_t)buf * HF_TILE_BYTES + r * 128u;
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float y0, y1;
+                upk2(mul2(pk2(b1[2 * e], b1[2 * e + 1]), T2), y0, y1);
+                split2(y0, y1, h[e], l[e]);
+            }
+            sts_u128(prow_a + (((uint32_t)(2 * hh) ^ key) << 4), h[0], h[1], h[2], h[3]);
+            sts_u128(prow_a + (((uint32_t)(2 * hh + 1) ^ key) << 4), h[4], h[5], h[6], h[7]);
+            sts_u128(prow_a + (((uint32_t)(4 + 2 * hh) ^ key) << 4), l[0], l[1], l[2], l[3]);
+            sts_u128(prow_a + (((uint32_t)(5 + 2 * hh) ^ key) << 4), l[4], l[5], l[6], l[7]);
+            fence_proxy_async();
+            tc_fence_before();
+            ws_parts_arrive();
+        };
+        if (n_my > 0) {
+            // the first tile's rows are split by the (otherwise idle) compute warps, 256 threads, while the service warps take tile 1
+            mbar_wait(bar_full, 0u);
+            const int node0 = tinfo_s[0], rows = tinfo_s[1];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int cp = tid + 256 * pp, row = cp >> 2, q4 = cp & 3;
+                float x[8];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (row < rows) { a = lds_f128(xs_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xs_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                float rm = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))), fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 1));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 2));
+                int ex = expo_above(rm);
+                ex = max(-100, min(110, ex));
+                const float s_row = pow2f(15 - ex);
+                if (q4 == 0) rowscale_s[row] = pow2f(ex - 15);
+                if (q4 == 0 && row < rows) atomicMax(gmax_s + group_of(gb_a, node0 + row, node0 + rows), __float_as_uint(rm));
+                const uint64_t S2 = pk2(s_row, s_row);
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float y0, y1;
+                    upk2(mul2(pk2(x[2 * e], x[2 * e + 1]), S2), y0, y1);
+                    split2(y0, y1, h[e], l[e]);
+                }
+                const uint32_t ra = smem_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
+                sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
+                sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
+            }
+            if (tid < rows) {
+                const uint4 m4 = lds_u128(op_a + (uint32_t)tid * 16u);
+                const unsigned int deg = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
+                if (deg > 0u) atomicMax(gdeg_s + group_of(gb_a, node0 + tid, node0 + rows), deg);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            ws_parts_arrive();     // -> the issue warp: X W group of tile 0
+            ws_compute_sync();     // the per-graph maxima of tile 0 are complete
+            mbar_wait(bar_w, 0u);
+        }
+        for (int j = 0; j < n_my; ++j) {
+            const int buf = j & 1;
+            const int rows = tinfo_s[buf * 4 + 1];
+            const int node0 = tinfo_s[buf * 4 + 0];
+            unsigned int* red = red_s + (j % 3) * 2;
+            (void)red;
+            // the graph of this thread's row: block-diagonal operator => its own scale per step
+            const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);
+            const float xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
+            const float dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
+            const float inv_si = rowscale_s[buf * 128 + r];
+            // the maxima of tile j + 2 go into the slot tile j - 1 used (last read a tile ago); the clears precede this warp's
+            // "tile complete" count, which the service warps wait for (all eight warps) before they split tile j + 2
+            if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
+            int e_tau[K];
+            {
+                float bet1 = 0.f, bet2 = 0.f;
+#pragma unroll
+                for (int k = K - 1; k >= 1; --k) {
+                    const float bet = xmax * hdr_s[1 + k] + dmax2 * bet1 + bet2;
+                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;
+                    e_tau[k] = max(30, min(240, e));
+                    bet2 = bet1;
+                    bet1 = bet;
+                }
+                e_tau[0] = 127;
+            }
+            // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), under the X W group
+            {
+                uint2 m2v = make_uint2(0u, 0u);
+                if ((int)r < rows) {
+                    const uint32_t src = op_a + (uint32_t)(buf * p.stage_bytes) + r * 16u + (uint32_t)hh * 8u;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m2v.x), "=r"(m2v.y) : "r"(src));
+                }
+#pragma unroll
+                for (int w2 = 0; w2 < 2; ++w2) {
+                    const uint32_t m = w2 ? m2v.y : m2v.x;
+                    uint32_t aw[16];
+#pragma unroll
+                    for (int b4 = 0; b4 < 8; ++b4) {
+                        uint2 v;
+                        const uint32_t idx = b4 == 0 ? ((m << 3) & 0x78u) : ((m >> (4 * b4 - 3)) & 0x78u);
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(lut_a + idx));
+                        aw[2 * b4] = v.x; aw[2 * b4 + 1] = v.y;
+                    }
+                    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + ADJ_COL + (uint32_t)(32 * hh + 16 * w2), aw);
+                }
+            }
+            // ---- X W done -> B_K-1 = P_K-1 / row scale
+            WPROBE(1);
+            mbar_wait(bar_mma, ph_mma);
+            WPROBE(2);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            const uint64_t I2 = pk2(inv_si, inv_si);
+            {
+                uint32_t v[16];
+                tmem_ld16(tmem_row + (uint32_t)(32 * (K - 1)), v);
+                tmem_wait_ld_();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    upk2(mul2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), I2), b1[2 * e], b1[2 * e + 1]);
+                    b2[2 * e] = 0.f; b2[2 * e + 1] = 0.f;
+                }
+            }
+            tmem_wait_st_();   // the adjacency stores have completed (first read by the first Clenshaw step's UMMAs)
+            split_arrive(buf, e_tau[K - 1]);
+            // ---- Clenshaw steps (two halves of 8 columns: 24 instead of 48 live accumulator registers)
+#pragma unroll
+            for (int k = K - 2; k >= 0; --k) {
+                const int e1 = e_tau[k + 1];
+                WPROBE(10 + k);
+                mbar_wait(bar_mma, ph_mma);
+                ph_mma ^= 1u;
+                tc_fence_after();
+                WPROBE(20 + k);
+                const float cfac = __uint_as_float((uint32_t)(e1 - 15 + (k > 0 ? 1 : 0)) << 23);   // (k > 0 ? 2 : 1) / tau_k+1
+                const uint64_t C2 = pk2(cfac, cfac);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t vp[8], vh[8], vl[8];
+                    tmem_ld8_(tmem_row + (uint32_t)(32 * k + 8 * half), vp);
+                    tmem_ld8_(tmem_row + (uint32_t)(32 * (k + 1) + 8 * half), vh);
+                    tmem_ld8_(tmem_row + (uint32_t)(32 * (k + 2) + 8 * half), vl);
+                    tmem_wait_ld_();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 8 * half + 2 * e;
+                        const uint64_t dv = sub2(pk2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1])), pk2(__uint_as_float(vl[2 * e]), __uint_as_float(vl[2 * e + 1])));
+                        const uint64_t bk = fma2(pk2(__uint_as_float(vp[2 * e]), __uint_as_float(vp[2 * e + 1])), I2, fma2(dv, C2, pk2(-b2[c], -b2[c + 1])));
+                        b2[c] = b1[c]; b2[c + 1] = b1[c + 1];
+                        upk2(bk, b1[c], b1[c + 1]);
+                    }
+                }
+                if (k > 0) split_arrive(buf, e_tau[k]);
+            }
+            // ---- every UMMA of this tile has completed and its accumulators are read: the next tile's X W group may be issued (its
+            // rows were split a tile ago) and this tile's part tile may be refilled with the rows of tile j + 2
+            WPROBE(30);
+            tc_fence_before();
+            if (j + 1 < n_my) { if (lane == 0) ws_poll(xs_count, 3 * (j + 2)); __syncwarp(); __threadfence_block(); }
+            if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int*>(pf_count), 1); }
+            ws_parts_arrive();
+            // ---- epilogue: unscale, bias, activation -> staging tile (the service warps store the rows)
+            {
+                const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+                const float inv_sw = hdr_s[0];
+                const uint64_t W2 = pk2(inv_sw, inv_sw);
+                float y[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 16 * hh + 4 * c);
+                    upk2(fma2(pk2(b1[4 * c], b1[4 * c + 1]), W2, pk2(bv.x, bv.y)), y[4 * c], y[4 * c + 1]);
+                    upk2(fma2(pk2(b1[4 * c + 2], b1[4 * c + 3]), W2, pk2(bv.z, bv.w)), y[4 * c + 2], y[4 * c + 3]);
+                }
+                if (p.act == MHO_ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], 0.f);
+                } else if (leaky_max) {
+                    const uint64_t SL2 = pk2(p.slope, p.slope);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float s0, s1;
+                        upk2(mul2(pk2(y[2 * e], y[2 * e + 1]), SL2), s0, s1);
+                        y[2 * e] = fmaxf(y[2 * e], s0); y[2 * e + 1] = fmaxf(y[2 * e + 1], s1);
+                    }
+                } else if (p.act == MHO_ACT_LEAKY) {
+                    const float sl = p.slope;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) y[e] = y[e] > 0.f ? y[e] : sl * y[e];
+                }
+                const uint32_t ya = xb_a + r * 128u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sts_f128(ya + (((uint32_t)(4 * hh + c) ^ key) << 4), make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]));
+                ws_out_arrive();   // (st.shared + bar.arrive / bar.sync + ld.shared: the documented producer-consumer pattern)
+                WPROBE(31);
+            }
+        }
+    } else if (warp < 11) {
+        // ======================================================= service warps =======================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int st = tid - 256;   // 0 .. 95
+        int4 ti_pref = make_int4(0, 0, 0, 0);
+        int g0_pref = 0, pref_j = -1;
+        auto prefetch_desc = [&](int j) {
+            if (j < n_my) {
+                ti_pref = __ldg(reinterpret_cast<const int4*>(p.b.tile_info) + ((int)blockIdx.x + j * G));
+                g0_pref = __ldg(p.b.tile_graph0 + ((int)blockIdx.x + j * G));
+                pref_j = j;
+            }
+        };
+        auto issue_load = [&](int j) {   // all of warp 8
+            const int buf = j & 1;
+            if (pref_j != j) prefetch_desc(j);
+            const int4 ti = ti_pref;
+            const int g0 = g0_pref;
+            prefetch_desc(j + 1);
+            const uint32_t fb = bar_full + 8u * buf;
+            const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
+            if (lane == 0) {
+                tinfo_s[buf * 4 + 0] = ti.x; tinfo_s[buf * 4 + 1] = ti.y; tinfo_s[buf * 4 + 2] = ti.z; tinfo_s[buf * 4 + 3] = ti.w;
+                const uint32_t xb = (uint32_t)ti.y * 128u;
+                mbar_expect_tx(fb, xb + (uint32_t)ti.y * 16u);
+                bulk_g2s(xs_a + (uint32_t)buf * HF_TILE_BYTES, p.X + (size_t)ti.x * 32, xb, fb);
+                bulk_g2s(opb, p.b.adj_bits + (size_t)ti.x * 4, (uint32_t)ti.y * 16u, fb);
+            }
+            for (int e = lane; e < 128; e += 32) {
+                const int gi = min(g0 + 1 + e, p.b.n_graphs);
+                cp_async4(gb_a + (uint32_t)(buf * 132 + e) * 4u, p.b.graph_off + gi);
+            }
+            cp_async_mbar_arrive(fb);
+        };
+        // rows of tile j -> part tile j & 1 (row-scaled), per-graph maxima of |x| and of the degree
+        auto x_split = [&](int j) {
+            const int buf = j & 1;
+            WPROBE(70);
+            mbar_wait(bar_full + 8u * buf, (uint32_t)((j >> 1) & 1));
+            WPROBE(71);
+            const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t opb = op_a + (uint32_t)(buf * p.stage_bytes);
+            const uint32_t gb = gb_a + (uint32_t)(buf * 132) * 4u;
+            for (int it = st; it < 512; it += 96) {   // (it >> 2 = row, 4 lanes per row; whole warps drop out together)
+                const int row = it >> 2, q4 = it & 3;
+                float x[8];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (row < rows) { a = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                float rm = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))), fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 1));
+                rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 2));
+                int ex = expo_above(rm);
+                ex = max(-100, min(110, ex));
+                const float s_row = pow2f(15 - ex);
+                if (q4 == 0) rowscale_s[buf * 128 + row] = pow2f(ex - 15);
+                if (q4 == 0 && row < rows) atomicMax(gmax_s + (j % 3) * 128 + group_of(gb, node0 + row, node0 + rows), __float_as_uint(rm));
+                const uint64_t S2 = pk2(s_row, s_row);
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float y0, y1;
+                    upk2(mul2(pk2(x[2 * e], x[2 * e + 1]), S2), y0, y1);
+                    split2(y0, y1, h[e], l[e]);
+                }
+                const uint32_t ra = parts_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
+                sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
+                sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
+            }
+            for (int row = st; row < rows; row += 96) {
+                const uint4 m4 = lds_u128(opb + (uint32_t)row * 16u);
+                const unsigned int deg = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
+                if (deg > 0u) atomicMax(gdeg_s + (j % 3) * 128 + group_of(gb, node0 + row, node0 + rows), deg);
+            }
+            fence_proxy_async();   // the part tile is read by the tensor core
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int*>(xs_count), 1); }
+            WPROBE(72);
+        };
+        if (warp == 8) {
+            if (n_my > 0) issue_load(0);
+            if (lane == 0) {
+                mbar_expect_tx(bar_w, (uint32_t)W_BYTES);
+                bulk_g2s(w_a, p.wimg, (uint32_t)W_BYTES, bar_w);
+            }
+            __syncwarp();
+            if (n_my > 1) issue_load(1);
+        }
+        for (int j = 0; j < n_my; ++j) {   // (tile 0 is split by the compute warps: the counter starts at 3)
+            const int buf = j & 1;
+            if (j + 1 < n_my) {
+                // part tile (j + 1) & 1 was last read by the UMMAs of tile j - 1; its maxima slots were cleared by the compute warps
+                if (j >= 1) { if (lane == 0) ws_poll(pf_count, 8 * j); __syncwarp(); __threadfence_block(); }
+                x_split(j + 1);
+            }
+            WPROBE(73);
+            ws_out_wait();   // the output rows of tile j are in the staging tile
+            WPROBE(74);
+            {
+                const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
+                const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+                float* dst = p.Y + (size_t)node0 * 32;
+                for (int c = st; c < rows * 8; c += 96) {
+                    const uint32_t row = (uint32_t)c >> 3, ch = (uint32_t)c & 7u;
+                    *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = lds_f128(xb_a + row * 128u + ((ch ^ (row & 7u)) << 4));
+                }
+            }
+            WPROBE(75);
+            ws_service_sync();   // the staging buffer (and its tile descriptor) may be refilled
+            if (warp == 8 && j + 2 < n_my) issue_load(j + 2);
+        }
+    } else {
+        // ========================================================= issue warp =========================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        auto issue_xw = [&](int buf) {
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            // P' = X' [W'_0 | ... | W'_K-1]:  x w ~ xh wh - xh wl' - xl' wh, two 16-wide K steps each
+            const uint32_t id_pos = idesc_f16((uint32_t)(32 * K), 0u, 0u), id_neg = idesc_f16((uint32_t)(32 * K), 0u, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tmem_base, desc_sw128(parts_a + 64u + 32u * ks), desc_sw128(w_a + 32u * ks), id_neg, ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tmem_base, desc_sw128(parts_a + 32u * ks), desc_sw128(w_a + 64u + 32u * ks), id_neg, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tmem_base, desc_sw128(parts_a + 32u * ks), desc_sw128(w_a + 32u * ks), id_pos, 1u);
+            umma_commit(bar_mma);
+        };
+        if (n_my > 0) {
+            ws_parts_wait();   // tile 0's rows are split (compute warps)
+            if (lane == 0) { mbar_wait(bar_w, 0u); tc_fence_after(); issue_xw(0); }
+            __syncwarp();
+        }
+        for (int j = 0; j < n_my; ++j) {
+            const int buf = j & 1;
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            for (int k = K - 2; k >= 0; --k) {
+                WPROBE(40 + k);
+                ws_parts_wait();   // the parts of B_k+1 are in place
+                WPROBE(50 + k);
+                if (lane == 0) {
+                    tc_fence_after();
+                    const int rows_t = tinfo_s[buf * 4 + 1];
+                    const uint32_t id_adj = idesc_f16(64u, 1u, 0u);
+                    const uint32_t d = tmem_base + (uint32_t)(32 * (k + 1));
+                    const int nks = (rows_t + 15) >> 4;   // 16-node slices beyond the tile's rows are all zero
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        if (ks == 0 || ks < nks) umma_f16_ts(d, tmem_base + ADJ_COL + (uint32_t)(ks * 8), desc_sw128(parts_a + (uint32_t)ks * 2048u), id_adj, ks > 0 ? 1u : 0u);
+                    umma_commit(bar_mma);
+                }
+                __syncwarp();
+                WPROBE(60 + k);
+            }
+            WPROBE(65);
+            ws_parts_wait();       // tile j's accumulators are consumed (and the compute warps have seen the rows of tile j + 1 split)
+            WPROBE(66);
+            if (j + 1 < n_my && lane == 0) { tc_fence_after(); issue_xw(buf ^ 1); }
+            __syncwarp();
+            WPROBE(67);
+        }
+    }
+#ifdef MHO_PROBE
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        const long long base = wprobe_s[0] >> 8;
+        for (int i = 0; i < 256; ++i) {
+            if (wprobe_s[i] == 0) continue;
+            printf("%s id %2d  t %7lld\n", i < 88 ? "t0  " : i < 176 ? "t256" : "t352", (int)(wprobe_s[i] & 255), (wprobe_s[i] >> 8) - base);
+        }
+    }
+#endif
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+}
+
+template <int K>
+cudaError_t launch_ws(const HfParams& p, size_t smem, int grid, cudaStream_t st) {
+    static int smem_set[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((int)smem > smem_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(cheb_f16ws_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[dev & 63] = (int)smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static int no_pdl = -1;
+    if (no_pdl < 0) { const char* e = getenv("MHO_NO_PDL"); no_pdl = e ? atoi(e) : 0; }
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, cheb_f16ws_kernel<K>, p);
+}
+
 template <int K, bool TRACK>
 cudaError_t launch_k(const HfParams& p, size_t smem, int grid, cudaStream_t st) {
     static int smem_set[64] = {0};
@@ -720,6 +1224,16 @@ cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int 
     int grid = num_sms * (K <= 5 ? 2 : 1);   // (one CTA per SM per launch + more streams was measured: no gain)
     if (grid > p.b.n_tiles) grid = p.b.n_tiles;
     if (grid < 1) grid = 1;
+    static int ws_env = -1;
+    if (ws_env < 0) { const char* e = getenv("MHO_WS"); ws_env = e ? atoi(e) : 1; }   // MHO_WS=0: the eight-warp kernel for every shape
+    if (ws_env && K <= 5 && p.use_bits && p.b.tile_graph0 != nullptr && !track_env) {
+        switch (K) {
+            case 2: return launch_ws<2>(p, smem, grid, st);
+            case 3: return launch_ws<3>(p, smem, grid, st);
+            case 4: return launch_ws<4>(p, smem, grid, st);
+            default: return launch_ws<5>(p, smem, grid, st);
+        }
+    }
     switch (K) {
         case 2: return track_env ? launch_k<2, true>(p, smem, grid, st) : launch_k<2, false>(p, smem, grid, st);
         case 3: return track_env ? launch_k<3, true>(p, smem, grid, st) : launch_k<3, false>(p, smem, grid, st);
