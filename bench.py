@@ -510,7 +510,7 @@ def run_gpu_arm(args):
         series["forward_backward_K%d_32_32" % w["K"]] = {
             "value": world * args.graphs / (train_ms * 1e-3), "unit": "graph forward+VJP steps/s (per-graph gradients + their deterministic sum)",
             "ms_per_step": train_ms, "ms_per_step_one_stream": train1_ms, "streams": n_tr, "launches_per_step": train_launches / nt,
-            "kernels": "cheb_f16_kernel (forward), cheb_backward_f16_kernel (tensor-core VJP), grads_sum_fused"}
+            "kernels": "cheb_f16ws_kernel (forward), cheb_backward_f16_kernel (tensor-core VJP), grads_sum_fused"}
         del gtt, gt1
         # ---- gradient exchange of AdHoc_train (gnn_offloading_agent.py:156-169 site): NCCL on device tensors
         if world > 1:
@@ -537,7 +537,7 @@ def run_gpu_arm(args):
                     ab_ = bytes_of(ws_)
                     pts.append({"n": n_, "K": K_, "B": B_, "ms_per_step": t_ / st_, "graph_steps_per_s": world * B_ * st_ / (t_ * 1e-3),
                                 "frac_of_hbm_roofline": ab_ * st_ / (t_ * 1e-3) / 1e9 / peak,
-                                "kernel": "cheb_f16_kernel" if n_ <= 128 else "cheb_forward_kernel (CSR walk)"})
+                                "kernel": ("cheb_f16ws_kernel" if K_ <= 5 else "cheb_f16_kernel") if n_ <= 128 else "cheb_forward_kernel (CSR walk)"})
                     del net_s, keep
                     torch.cuda.empty_cache()
         series["sweep"] = {"unit": UNIT, "points": pts,
@@ -577,7 +577,7 @@ def run_gpu_arm(args):
                     "steps": e2e_steps, "api": "mho_cheb_forward_host_async + mho_host_wait, two steps in flight (page-locked host buffers from mho_host_alloc; every step uploads X + CSR and downloads Y; chunked upload/kernel/download pipeline)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "cheb_f16_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "cheb_f16ws_kernel<K> (K <= 5; cheb_f16_kernel<K> for K > 5)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes_survey_formula": bytes_of(w, True),
                          "frac_survey_formula": bytes_of(w, True) / (per_launch_ms * 1e-3) / 1e9 / peak,
