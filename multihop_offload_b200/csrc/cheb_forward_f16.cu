@@ -8,22 +8,23 @@
 // re-engineered around what the first kernel's profile showed (28 % tensor pipe, 57 % issue slots, 18 k warp
 // instructions per tile):
 //   * fp32 operands travel as TWO fp16 parts (x = h - l', h = rn16(x), l' = rn16(h - x): 22 significand bits) after a
-//     power-of-two scale per tile and per Clenshaw step that keeps every part inside fp16's range.  The scales come
-//     from an upper bound of max |B_k| (tile max |X|, per-k weight norms from the prepared image, the tile's max degree;
+//     power-of-two scale per GRAPH and per Clenshaw step that keeps every part inside fp16's range.  The scales come
+//     from an upper bound of max |B_k| (graph max |X|, per-k weight norms from the prepared image, the graph's max degree;
 //     for K > 5 the running maxima of |B_k| themselves), never from the data of the step itself: no extra barrier.
 //     X W needs 3 part products instead of 6 (h h, h l, l h; 2^-22), the adjacency UMMA has N = 64 instead of 96, a
 //     split costs 2 instructions per element (F2FP + FHADD, mixed-precision subtract) instead of 5.5.
 //   * one thread owns 16 accumulator columns of its row (8 compute warps per tile instead of 16): per-thread overheads
 //     (addresses, waits, fences, loop control) are paid once per 16 elements.
-//   * a ninth warp is the control warp: its lane 0 issues every tcgen05.mma and the 1-D bulk copies
-//     (cp.async.bulk -> mbarrier complete_tx) that bring the NEXT tile's input rows and adjacency bit rows into the
-//     other staging buffer; compute warps and control warp meet only through mbarriers (parts_ready / mma_done /
-//     full / empty) - no __syncthreads in the steady state, no global-memory scheduler state.
+//   * all warps of the eight-warp kernel meet at a hardware named barrier; thread 0 then issues the UMMA group and commits
+//     to one mbarrier every thread waits on; warp 0 also issues the 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx)
+//     that bring the NEXT tile's input rows and adjacency bit rows into the other staging buffer.  (A ninth, dedicated issuer
+//     warp costs two CTAs per SM their registers; the warp-specialised variant further down - cheb_f16ws_kernel, 12 warps
+//     with setmaxnreg - is what K <= 5 batches with bit rows run through.)
 //   * the adjacency products are never accumulated onto P_k (the per-step scale differs): the UMMA overwrites two
 //     consumed column blocks, so nothing has to be cleared.
 // Tensor memory: K * 32 columns P, 32 spare, 64 adjacency (fp16 pairs) = 256 for K <= 5 -> two CTAs per SM; the tensor
-// pipe sees two independent issuers (one per CTA), which is what lifts it above one UMMA per ~48 cycles (measured,
-// tools/umma_probe2.cu).
+// pipe sees two independent issuers (one per CTA).  Measured cost of this UMMA (tools/umma_probe3.cu): 57-63 cycles on an
+// idle GPU, 84 with every SM busy.
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdio>
