@@ -139,3 +139,39 @@ def test_repeatable_and_independent_of_grid(torch_cuda):
     a, sa = _run(torch_cuda, 5, O.ACT_LEAKY, ws, mats, X, dY)
     b, sb = _run(torch_cuda, 5, O.ACT_LEAKY, ws, mats, X, dY)
     assert np.array_equal(a, b) and np.array_equal(sa, sb)
+
+
+def test_long_pipelines_many_graphs_per_cta(torch_cuda):
+    """4096 graphs = fourteen graphs per CTA pass through the VJP kernel's role hand-offs; every 16th graph against the
+    fp64 oracle, the deterministic sum against the sum of the per-graph rows, and bit-identical on a second run."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from multihop_offload_b200 import ChebNet, GraphBatch, LayerSpec
+    torch = torch_cuda
+    w = bench.make_workload(4096, 0, None, K=5)
+    net = ChebNet([LayerSpec(5, 32, 32, 2, 0.2)], device="cuda:0")
+    ws = [(w["W"], w["b"])]
+    net.set_weights(ws)
+    batch = GraphBatch(w["graph_off"], w["rowptr"], w["colidx"], None, device="cuda:0")
+    Xd = torch.from_numpy(w["X"]).cuda()
+    rng = np.random.default_rng(3)
+    dY = rng.normal(size=w["X"].shape).astype(np.float32)
+    Y, saved = net.forward(batch, Xd, save=True)
+    g1, s1, _ = net.backward(batch, Xd, Y, saved, torch.from_numpy(dY).cuda())
+    g2, s2, _ = net.backward(batch, Xd, Y, saved, torch.from_numpy(dY).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)
+    g1 = g1.cpu().numpy()
+    assert np.abs(s1.cpu().numpy() - g1.astype(np.float64).sum(0)).max() / np.abs(g1.astype(np.float64).sum(0)).max() < 1e-6
+    import scipy.sparse as sp
+    off, rp, ci = w["graph_off"], w["rowptr"], w["colidx"]
+    for gi in range(0, 4096, 16):
+        a, b = int(off[gi]), int(off[gi + 1])
+        n = b - a
+        indptr = rp[a:b + 1] - rp[a]
+        A = sp.csr_matrix((np.ones(int(indptr[-1])), ci[rp[a]:rp[b]] - a, indptr), shape=(n, n))
+        ref = _oracle([A], w["X"][a:b].astype(np.float64), ws, O.ACT_LEAKY, dY[a:b].astype(np.float64))[0]
+        e, k = _block_err(g1[gi], ref, 5)
+        assert e < GTOL, (gi, k, e)

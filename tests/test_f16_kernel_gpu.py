@@ -214,3 +214,36 @@ def test_forward_after_optimizer_replay_uses_new_weights(torch_cuda):
         assert np.abs(Y1 - Y0).max() > 1e-4 * np.abs(Y0).max(), "the update must change the output"
         tol = TOL if len(specs) == 1 or specs[0].K == 1 else 5e-5   # deep K > 1 stacks: fp32 round-off amplification
         assert rel_err(Y1, ref1, batch.graph_off, zs) < tol, [s.K for s in specs]
+
+
+def test_long_pipelines_many_tiles_per_cta(torch_cuda):
+    """8192 graphs = ~4750 tiles: sixteen tiles per CTA through the warp-specialised kernel's hand-offs (named barriers,
+    monotonic counters, double-buffered staging), and the same batch through the eight-warp kernel path (CSR input) -
+    against the plain-C oracle, K = 5 and K = 3."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import c_oracle
+    from multihop_offload_b200 import ChebNet, GraphBatch, LayerSpec
+    for K in (5, 3):
+        w = bench.make_workload(8192, 0, None, K=K)
+        ws = [(w["W"], w["b"])]
+        ref = c_oracle.stack_forward(w["graph_off"], w["rowptr"], w["colidx"], None, ws, [2], 0.2, w["X"].astype(np.float64), 0)
+        net = ChebNet([LayerSpec(K, 32, 32, 2, 0.2)], device="cuda:0")
+        net.set_weights(ws)
+        Xd = torch_cuda.from_numpy(w["X"]).cuda()
+        outs = []
+        for bits in (True, False):
+            batch = GraphBatch(w["graph_off"], w["rowptr"], w["colidx"], None, device="cuda:0")
+            if not bits:
+                batch.dev.pop("adj_bits", None)
+                batch._struct_cache = {}
+            Y = net.forward(batch, Xd)
+            Yb = net.forward(batch, Xd)
+            assert torch_cuda.equal(Y, Yb)
+            outs.append(Y.cpu().numpy())
+        off = w["graph_off"]
+        den = np.maximum.reduceat(np.abs(ref).max(axis=1), off[:-1].astype(np.int64))
+        for Y in outs:
+            err = np.maximum.reduceat(np.abs(Y - ref).max(axis=1), off[:-1].astype(np.int64)) / den
+            assert err.max() < TOL, (K, err.max(), int(err.argmax()))
+        assert np.array_equal(outs[0], outs[1]), "the two kernels run the same arithmetic"
