@@ -900,37 +900,12 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             if (j + 1 < n_my) { if (lane == 0) ws_poll(xs_count, 3 * (j + 2)); __syncwarp(); __threadfence_block(); }
             if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int*>(pf_count), 1); }
             ws_parts_arrive();
-            // ---- epilogue: unscale, bias, activation -> staging tile (the service warps store the rows)
+            // ---- B_0 (still in units of the weight scale) -> staging tile; the service warps un-scale, add the bias, apply the
+            // activation and store the rows
             {
-                const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
-                const float inv_sw = hdr_s[0];
-                const uint64_t W2 = pk2(inv_sw, inv_sw);
-                float y[16];
+                const uint32_t ya = xs_a + (uint32_t)buf * HF_TILE_BYTES + r * 128u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 16 * hh + 4 * c);
-                    upk2(fma2(pk2(b1[4 * c], b1[4 * c + 1]), W2, pk2(bv.x, bv.y)), y[4 * c], y[4 * c + 1]);
-                    upk2(fma2(pk2(b1[4 * c + 2], b1[4 * c + 3]), W2, pk2(bv.z, bv.w)), y[4 * c + 2], y[4 * c + 3]);
-                }
-                if (p.act == MHO_ACT_RELU) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], 0.f);
-                } else if (leaky_max) {
-                    const uint64_t SL2 = pk2(p.slope, p.slope);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float s0, s1;
-                        upk2(mul2(pk2(y[2 * e], y[2 * e + 1]), SL2), s0, s1);
-                        y[2 * e] = fmaxf(y[2 * e], s0); y[2 * e + 1] = fmaxf(y[2 * e + 1], s1);
-                    }
-                } else if (p.act == MHO_ACT_LEAKY) {
-                    const float sl = p.slope;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) y[e] = y[e] > 0.f ? y[e] : sl * y[e];
-                }
-                const uint32_t ya = xb_a + r * 128u;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sts_f128(ya + (((uint32_t)(4 * hh + c) ^ key) << 4), make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]));
+                for (int c = 0; c < 4; ++c) sts_f128(ya + (((uint32_t)(4 * hh + c) ^ key) << 4), make_float4(b1[4 * c], b1[4 * c + 1], b1[4 * c + 2], b1[4 * c + 3]));
                 ws_out_arrive();   // (st.shared + bar.arrive / bar.sync + ld.shared: the documented producer-consumer pattern)
                 WPROBE(31);
             }
@@ -1033,15 +1008,31 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
                 x_split(j + 1);
             }
             WPROBE(73);
-            ws_out_wait();   // the output rows of tile j are in the staging tile
+            ws_out_wait();   // the rows of B_0 of tile j are in the staging tile
             WPROBE(74);
             {
                 const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
                 const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
                 float* dst = p.Y + (size_t)node0 * 32;
+                const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
+                const float inv_sw = bias_s[32];
+                const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
                 for (int c = st; c < rows * 8; c += 96) {
                     const uint32_t row = (uint32_t)c >> 3, ch = (uint32_t)c & 7u;
-                    *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = lds_f128(xb_a + row * 128u + ((ch ^ (row & 7u)) << 4));
+                    const float4 v = lds_f128(xb_a + row * 128u + ((ch ^ (row & 7u)) << 4));
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * ch);
+                    float y[4] = {fmaf(v.x, inv_sw, bv.x), fmaf(v.y, inv_sw, bv.y), fmaf(v.z, inv_sw, bv.z), fmaf(v.w, inv_sw, bv.w)};
+                    if (p.act == MHO_ACT_RELU) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+                    } else if (leaky_max) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], y[e] * p.slope);
+                    } else if (p.act == MHO_ACT_LEAKY) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) y[e] = y[e] > 0.f ? y[e] : p.slope * y[e];
+                    }
+                    *reinterpret_cast<float4*>(dst + (size_t)row * 32 + ch * 4) = make_float4(y[0], y[1], y[2], y[3]);
                 }
             }
             WPROBE(75);
