@@ -641,13 +641,17 @@ __global__ void __launch_bounds__(HF_THREADS, (K <= 5 ? 2 : 1)) cheb_f16_kernel(
 // dependent chain of a tile moved off the eight compute warps (12 warps per CTA, two CTAs per SM, register budgets re-balanced
 // with setmaxnreg):
 //   * warps 0-7, COMPUTE (thread = one row x 16 columns): adjacency expansion under the X W group, then per round trip: wait,
-//     tensor-memory load, recurrence in packed fp32, split, arrive; the output rows go to the staging tile and are left there.
-//   * warps 8-10, SERVICE (96 threads): bulk loads two tiles ahead, the row split of the NEXT tile (per-row scales, per-graph
-//     maxima), the coalesced output store of the CURRENT tile.
+//     tensor-memory load, recurrence in packed fp32, split, arrive; the rows of the NEXT tile are split inside the wait
+//     windows of two Clenshaw steps (the windows are ~1 k cycles: the UMMA group under load); B_0 goes to the staging tile raw.
+//   * warps 8-10, SERVICE (96 threads): bulk loads two tiles ahead; un-scale, bias, activation and the coalesced output store
+//     of the CURRENT tile.
 //   * warp 11, ISSUE: one thread issues every tcgen05.mma group (an issuing thread stalls until the tensor pipe has accepted the
 //     group: 50-130 cycles per UMMA with two CTAs sharing the pipe).
 // Hand-offs: named barriers with fixed arrive / sync counts where the two sides alternate strictly (parts ready: 256 + 32, output
-// rows staged: 256 + 96), monotonic shared-memory counters where one side may run ahead (rows split, part tile free).
+// rows staged: 256 + 96).  For K >= 4 (template flag S_SPLIT) the service warps also split the next tile's rows - measured 5 %
+// faster on the benchmark layer - with monotonic shared-memory counters for "rows split" / "part tile free" (one side may run
+// ahead there); 96 threads need ~7 k cycles for a tile's rows, more than a K <= 3 tile lasts, so those keep the split in the
+// compute warps' wait windows.
 __device__ __forceinline__ void ws_parts_arrive() { asm volatile("bar.arrive 1, 288;" ::: "memory"); }
 __device__ __forceinline__ void ws_parts_wait() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
 __device__ __forceinline__ void ws_out_arrive() { asm volatile("bar.arrive 2, 352;" ::: "memory"); }
@@ -662,7 +666,7 @@ __device__ __forceinline__ void tmem_ld8_(uint32_t taddr, uint32_t (&r)[8]) {
                  : "memory");
 }
 
-template <int K>
+template <int K, bool S_SPLIT>
 __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constant__ HfParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int W_BYTES = hf_w_bytes(K);
@@ -687,11 +691,11 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
     unsigned char* grp_s = op_s + 2 * p.stage_bytes;
     const uint32_t smem_a = smem_u32(smem), xs_a = smem_a + 2u * HF_TILE_BYTES, w_a = smem_u32(w_s), ctl_a = smem_u32(ctl_s), lut_a = smem_u32(lut_s),
                    op_a = smem_u32(op_s);
-    // control block: full[2] +0, weights +32, mma +40, tmem slot +48, rows-split counter +56, part-tile-free counter +60, tile info +64
+    // control block: full[2] +0, weights +32, mma +40, tmem slot +48, tile info +64
     // ([buf][4]), reductions +96 ([3][2]), row scales +512 ([2][128] floats)
     const uint32_t bar_full = ctl_a, bar_w = ctl_a + 32, bar_mma = ctl_a + 40, tslot = ctl_a + 48;
-    volatile int* xs_count = reinterpret_cast<volatile int*>(ctl_s + 56);   // + 3 per tile whose rows are split (service warps)
-    volatile int* pf_count = reinterpret_cast<volatile int*>(ctl_s + 60);   // + 8 per tile whose UMMAs are all complete (compute warps)
+    volatile int* xs_count = reinterpret_cast<volatile int*>(ctl_s + 56);   // S_SPLIT: + 3 per tile whose rows are split (service warps)
+    volatile int* pf_count = reinterpret_cast<volatile int*>(ctl_s + 60);   // S_SPLIT: + 8 per tile whose UMMAs are all complete (compute warps)
     volatile int* tinfo_s = reinterpret_cast<volatile int*>(ctl_s + 64);
     unsigned int* red_s = reinterpret_cast<unsigned int*>(ctl_s + 96);
     float* rowscale_s = reinterpret_cast<float*>(ctl_s + 512);
@@ -707,7 +711,7 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
         mbar_init(bar_full + 8, 33u);
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
-        *xs_count = 3;
+        *xs_count = 3;   // (tile 0 is split by the compute warps)
         *pf_count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -755,16 +759,22 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             tc_fence_before();
             ws_parts_arrive();
         };
-        if (n_my > 0) {
-            // the first tile's rows are split by the (otherwise idle) compute warps, 256 threads, while the service warps take tile 1
-            mbar_wait(bar_full, 0u);
-            const int node0 = tinfo_s[0], rows = tinfo_s[1];
+        // rows of tile j -> part tile j & 1 (row-scaled), per-graph maxima of |x| and of the degree.  part 0 / 1: the two halves of the
+        // rows (one wait window of a Clenshaw step each), part 1 also the degrees; part 2: everything
+        auto x_split = [&](int j, int part) {
+            const int buf = j & 1;
+            if (part != 1) mbar_wait(bar_full + 8u * buf, (uint32_t)((j >> 1) & 1));
+            const int node0 = tinfo_s[buf * 4 + 0], rows = tinfo_s[buf * 4 + 1];
+            const uint32_t parts_a = smem_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t xb_a = xs_a + (uint32_t)buf * HF_TILE_BYTES;
+            const uint32_t gb = gb_a + (uint32_t)(buf * 132) * 4u;
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
+                if (part != 2 && part != pp) continue;
                 const int cp = tid + 256 * pp, row = cp >> 2, q4 = cp & 3;
                 float x[8];
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (row < rows) { a = lds_f128(xs_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xs_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
+                if (row < rows) { a = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u); b = lds_f128(xb_a + (uint32_t)row * 128u + (uint32_t)q4 * 32u + 16u); }
                 x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
                 float rm = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))), fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
                 rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, 1));
@@ -772,8 +782,8 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
                 int ex = expo_above(rm);
                 ex = max(-100, min(110, ex));
                 const float s_row = pow2f(15 - ex);
-                if (q4 == 0) rowscale_s[row] = pow2f(ex - 15);
-                if (q4 == 0 && row < rows) atomicMax(gmax_s + group_of(gb_a, node0 + row, node0 + rows), __float_as_uint(rm));
+                if (q4 == 0) rowscale_s[buf * 128 + row] = pow2f(ex - 15);
+                if (q4 == 0 && row < rows) atomicMax(gmax_s + (j % 3) * 128 + group_of(gb, node0 + row, node0 + rows), __float_as_uint(rm));
                 const uint64_t S2 = pk2(s_row, s_row);
                 uint32_t h[4], l[4];
 #pragma unroll
@@ -782,48 +792,27 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
                     upk2(mul2(pk2(x[2 * e], x[2 * e + 1]), S2), y0, y1);
                     split2(y0, y1, h[e], l[e]);
                 }
-                const uint32_t ra = smem_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
+                const uint32_t ra = parts_a + (uint32_t)row * 128u, rk = (uint32_t)row & 7u;
                 sts_u128(ra + (((uint32_t)q4 ^ rk) << 4), h[0], h[1], h[2], h[3]);
                 sts_u128(ra + (((4u + (uint32_t)q4) ^ rk) << 4), l[0], l[1], l[2], l[3]);
             }
-            if (tid < rows) {
-                const uint4 m4 = lds_u128(op_a + (uint32_t)tid * 16u);
+            if (part != 0 && tid < rows) {
+                const uint4 m4 = lds_u128(op_a + (uint32_t)(buf * p.stage_bytes) + (uint32_t)tid * 16u);
                 const unsigned int deg = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
-                if (deg > 0u) atomicMax(gdeg_s + group_of(gb_a, node0 + tid, node0 + rows), deg);
+                if (deg > 0u) atomicMax(gdeg_s + (j % 3) * 128 + group_of(gb, node0 + tid, node0 + rows), deg);
             }
-            fence_proxy_async();
+            fence_proxy_async();   // the part tile is read by the tensor core
+        };
+        if (n_my > 0) {
+            x_split(0, 2);
             tc_fence_before();
             ws_parts_arrive();     // -> the issue warp: X W group of tile 0
-            ws_compute_sync();     // the per-graph maxima of tile 0 are complete
             mbar_wait(bar_w, 0u);
         }
         for (int j = 0; j < n_my; ++j) {
             const int buf = j & 1;
             const int rows = tinfo_s[buf * 4 + 1];
             const int node0 = tinfo_s[buf * 4 + 0];
-            unsigned int* red = red_s + (j % 3) * 2;
-            (void)red;
-            // the graph of this thread's row: block-diagonal operator => its own scale per step
-            const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);
-            const float xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
-            const float dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
-            const float inv_si = rowscale_s[buf * 128 + r];
-            // the maxima of tile j + 2 go into the slot tile j - 1 used (last read a tile ago); the clears precede this warp's
-            // "tile complete" count, which the service warps wait for (all eight warps) before they split tile j + 2
-            if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
-            int e_tau[K];
-            {
-                float bet1 = 0.f, bet2 = 0.f;
-#pragma unroll
-                for (int k = K - 1; k >= 1; --k) {
-                    const float bet = xmax * hdr_s[1 + k] + dmax2 * bet1 + bet2;
-                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;
-                    e_tau[k] = max(30, min(240, e));
-                    bet2 = bet1;
-                    bet1 = bet;
-                }
-                e_tau[0] = 127;
-            }
             // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), under the X W group
             {
                 uint2 m2v = make_uint2(0u, 0u);
@@ -851,6 +840,28 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             WPROBE(2);
             ph_mma ^= 1u;
             tc_fence_after();
+            // the X W group was issued after EVERY compute thread had split its share of this tile's rows: the per-graph maxima and
+            // the row scales are complete.  The graph of this thread's row: block-diagonal operator => its own scale per step
+            const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);
+            const float xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
+            const float dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
+            const float inv_si = rowscale_s[buf * 128 + r];
+            // the maxima of tile j + 2 go into the slot tile j - 1 used; they are collected during tile j + 1, i.e. after the X W
+            // group of tile j + 1, which every thread arrives for after these clears
+            if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
+            int e_tau[K];
+            {
+                float bet1 = 0.f, bet2 = 0.f;
+#pragma unroll
+                for (int kk = K - 1; kk >= 1; --kk) {
+                    const float bet = xmax * hdr_s[1 + kk] + dmax2 * bet1 + bet2;
+                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;
+                    e_tau[kk] = max(30, min(240, e));
+                    bet2 = bet1;
+                    bet1 = bet;
+                }
+                e_tau[0] = 127;
+            }
             const uint64_t I2 = pk2(inv_si, inv_si);
             {
                 uint32_t v[16];
@@ -867,6 +878,14 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             // ---- Clenshaw steps (two halves of 8 columns: 24 instead of 48 live accumulator registers)
 #pragma unroll
             for (int k = K - 2; k >= 0; --k) {
+                // the next tile's input rows are split into the other part tile inside the wait windows
+                if (S_SPLIT) {
+                } else if (K >= 4) {
+                    if (k == K - 3 && j + 1 < n_my) x_split(j + 1, 0);
+                    if (k == K - 4 && j + 1 < n_my) x_split(j + 1, 1);
+                } else if (k == (K == 3 ? 1 : 0) && j + 1 < n_my) {
+                    x_split(j + 1, 2);
+                }
                 const int e1 = e_tau[k + 1];
                 WPROBE(10 + k);
                 mbar_wait(bar_mma, ph_mma);
@@ -897,8 +916,12 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             // rows were split a tile ago) and this tile's part tile may be refilled with the rows of tile j + 2
             WPROBE(30);
             tc_fence_before();
-            if (j + 1 < n_my) { if (lane == 0) ws_poll(xs_count, 3 * (j + 2)); __syncwarp(); __threadfence_block(); }
-            if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int*>(pf_count), 1); }
+            if (S_SPLIT) {
+                // the service warps split the next tile's rows: they must be done before its X W group is issued, and they may refill
+                // this tile's part tile (rows of tile j + 2) once every warp has counted here
+                if (j + 1 < n_my) { if (lane == 0) ws_poll(xs_count, 3 * (j + 2)); __syncwarp(); __threadfence_block(); }
+                if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int*>(pf_count), 1); }
+            }
             ws_parts_arrive();
             // ---- B_0 (still in units of the weight scale) -> staging tile; the service warps un-scale, add the bias, apply the
             // activation and store the rows
@@ -945,7 +968,7 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             cp_async_mbar_arrive(fb);
         };
         // rows of tile j -> part tile j & 1 (row-scaled), per-graph maxima of |x| and of the degree
-        auto x_split = [&](int j) {
+        auto x_split_s = [&](int j) {
             const int buf = j & 1;
             WPROBE(70);
             mbar_wait(bar_full + 8u * buf, (uint32_t)((j >> 1) & 1));
@@ -1000,12 +1023,12 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             __syncwarp();
             if (n_my > 1) issue_load(1);
         }
-        for (int j = 0; j < n_my; ++j) {   // (tile 0 is split by the compute warps: the counter starts at 3)
+        for (int j = 0; j < n_my; ++j) {
             const int buf = j & 1;
-            if (j + 1 < n_my) {
+            if (S_SPLIT && j + 1 < n_my) {
                 // part tile (j + 1) & 1 was last read by the UMMAs of tile j - 1; its maxima slots were cleared by the compute warps
                 if (j >= 1) { if (lane == 0) ws_poll(pf_count, 8 * j); __syncwarp(); __threadfence_block(); }
-                x_split(j + 1);
+                x_split_s(j + 1);
             }
             WPROBE(73);
             ws_out_wait();   // the rows of B_0 of tile j are in the staging tile
@@ -1105,13 +1128,13 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
     if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
-template <int K>
+template <int K, bool S_SPLIT>
 cudaError_t launch_ws(const HfParams& p, size_t smem, int grid, cudaStream_t st) {
     static int smem_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if ((int)smem > smem_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(cheb_f16ws_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(cheb_f16ws_kernel<K, S_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set[dev & 63] = (int)smem;
     }
@@ -1128,7 +1151,7 @@ cudaError_t launch_ws(const HfParams& p, size_t smem, int grid, cudaStream_t st)
     static int no_pdl = -1;
     if (no_pdl < 0) { const char* e = getenv("MHO_NO_PDL"); no_pdl = e ? atoi(e) : 0; }
     cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, cheb_f16ws_kernel<K>, p);
+    return cudaLaunchKernelEx(&cfg, cheb_f16ws_kernel<K, S_SPLIT>, p);
 }
 
 template <int K, bool TRACK>
@@ -1220,10 +1243,12 @@ cudaError_t cheb_f16_launch(const FwdParams& fp, const unsigned char* wimg, int 
     if (ws_env < 0) { const char* e = getenv("MHO_WS"); ws_env = e ? atoi(e) : 1; }   // MHO_WS=0: the eight-warp kernel for every shape
     if (ws_env && K <= 5 && p.use_bits && p.b.tile_graph0 != nullptr && !track_env) {
         switch (K) {
-            case 2: return launch_ws<2>(p, smem, grid, st);
-            case 3: return launch_ws<3>(p, smem, grid, st);
-            case 4: return launch_ws<4>(p, smem, grid, st);
-            default: return launch_ws<5>(p, smem, grid, st);
+            // who splits the next tile's rows: the compute warps inside their wait windows (short tiles: the 96 service threads need
+            // ~7 k cycles for a tile's rows), or the service warps (K >= 4: 5 % faster on the benchmark layer)
+            case 2: return launch_ws<2, false>(p, smem, grid, st);
+            case 3: return launch_ws<3, false>(p, smem, grid, st);
+            case 4: return launch_ws<4, true>(p, smem, grid, st);
+            default: return launch_ws<5, true>(p, smem, grid, st);
         }
     }
     switch (K) {
