@@ -42,7 +42,6 @@
 
 namespace {
 
-constexpr int BF_COMPUTE = 256;
 constexpr int BF_THREADS = 384;
 constexpr uint32_t BF_TCOLS = 256u, BF_ADJ_COL = 192u, BF_DW_COL = 64u;
 

@@ -657,7 +657,6 @@ __device__ __forceinline__ void ws_parts_wait() { asm volatile("bar.sync 1, 288;
 __device__ __forceinline__ void ws_out_arrive() { asm volatile("bar.arrive 2, 352;" ::: "memory"); }
 __device__ __forceinline__ void ws_out_wait() { asm volatile("bar.sync 2, 352;" ::: "memory"); }
 __device__ __forceinline__ void ws_service_sync() { asm volatile("bar.sync 3, 96;" ::: "memory"); }
-__device__ __forceinline__ void ws_compute_sync() { asm volatile("bar.sync 4, 256;" ::: "memory"); }
 __device__ __forceinline__ void ws_poll(volatile int* c, int target) { while (*c < target) { } }
 __device__ __forceinline__ void tmem_ld8_(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -738,7 +737,6 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
         const uint32_t key = r & 7u;
         const float* bias_s = reinterpret_cast<const float*>(w_s + (size_t)K * 32 * 128);
         const float* hdr_s = bias_s + 32;
-        const bool leaky_max = p.act == MHO_ACT_LEAKY && p.slope >= 0.f && p.slope <= 1.f;
         uint32_t ph_mma = 0;
         float b1[16], b2[16];
         auto split_arrive = [&](int buf, int e1) {

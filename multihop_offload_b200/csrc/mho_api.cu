@@ -523,7 +523,7 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
         for (int i = 0; i < 2 * MHO_EV_PER_SLOT; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
     }
     cudaEvent_t* ev = c->ev + slot * MHO_EV_PER_SLOT;
-    cudaEvent_t ev_start = ev[2 * MHO_MAX_CHUNKS], ev_done = ev[2 * MHO_MAX_CHUNKS + 1];
+    cudaEvent_t ev_done = ev[2 * MHO_MAX_CHUNKS + 1];
     // the slot's previous user (two calls ago) must have finished its downloads before the buffers are recycled;
     // growing the slot frees device memory, which waits for the device anyway
     if (c->slot_used[slot]) CUDA_TRY(cudaEventSynchronize(ev_done));
@@ -542,7 +542,6 @@ static int forward_host_impl(mho_ctx_t* c, int32_t n_graphs, const int32_t* goff
     cudaStream_t sh = c->h2d_stream, sd = c->d2h_stream;
     // uploads may start as soon as the slot is free (checked above): they do NOT wait for the caller's stream, whose
     // pending work is the other slot's kernels
-    (void)ev_start;
     if (d_go) {
         // tile descriptors, graph offsets and first-graph indices are adjacent on the device: ONE staged (pageable) copy
         std::vector<int32_t> meta((al(b_ti) + al(b_go) + al(b_tg)) / 4, 0);
