@@ -177,6 +177,9 @@ class GraphBatch:
             return self.dev["adj_bits_graph"]
         import torch
         t = None
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            raise _lib.MhoError("GraphBatch: the per-graph bit rows of the tensor-core VJP are built (host) and uploaded on first use - "
+                                "run one backward (or batch.struct(per_graph_tiles=True)) on this batch before capturing a CUDA graph")
         if self.vals is None and self.n_graphs and self.total_nodes and self.max_graph_rows <= 128:
             if self.adj_bits is not None and self.n_tiles == self.n_graphs:
                 t = self.dev["adj_bits"]   # every tile is one graph
