@@ -811,6 +811,31 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             const int buf = j & 1;
             const int rows = tinfo_s[buf * 4 + 1];
             const int node0 = tinfo_s[buf * 4 + 0];
+            // per-thread scales of tile j: the graph of this thread's row (block-diagonal operator => its own scale per step), the
+            // row scale of X, the exponents of the Clenshaw bounds.  Needs every thread's share of the row split of tile j:
+            // S_SPLIT: complete since the end of tile j - 1 (counter); otherwise complete once the X W group has been issued
+            float inv_si = 0.f;
+            int e_tau[K];
+            auto tile_scales = [&]() {
+                const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);
+                const float xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
+                const float dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
+                inv_si = rowscale_s[buf * 128 + r];
+                // the maxima of tile j + 2 go into the slot tile j - 1 used; they are collected after every thread has arrived for
+                // the X W group of tile j + 1 (S_SPLIT: after every warp has counted this tile complete), i.e. after these clears
+                if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
+                float bet1 = 0.f, bet2 = 0.f;
+#pragma unroll
+                for (int kk = K - 1; kk >= 1; --kk) {
+                    const float bet = xmax * hdr_s[1 + kk] + dmax2 * bet1 + bet2;
+                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;
+                    e_tau[kk] = max(30, min(240, e));
+                    bet2 = bet1;
+                    bet1 = bet;
+                }
+                e_tau[0] = 127;
+            };
+            if (S_SPLIT) tile_scales();
             // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), under the X W group
             {
                 uint2 m2v = make_uint2(0u, 0u);
@@ -838,28 +863,7 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             WPROBE(2);
             ph_mma ^= 1u;
             tc_fence_after();
-            // the X W group was issued after EVERY compute thread had split its share of this tile's rows: the per-graph maxima and
-            // the row scales are complete.  The graph of this thread's row: block-diagonal operator => its own scale per step
-            const int g = group_of(gb_a + (uint32_t)(buf * 132) * 4u, node0 + min((int)r, rows - 1), node0 + rows);
-            const float xmax = __uint_as_float(gmax_s[(j % 3) * 128 + g]);
-            const float dmax2 = 2.f * (float)gdeg_s[(j % 3) * 128 + g];
-            const float inv_si = rowscale_s[buf * 128 + r];
-            // the maxima of tile j + 2 go into the slot tile j - 1 used; they are collected during tile j + 1, i.e. after the X W
-            // group of tile j + 1, which every thread arrives for after these clears
-            if (tid < 128) { gmax_s[((j + 2) % 3) * 128 + tid] = 0u; gdeg_s[((j + 2) % 3) * 128 + tid] = 0u; }
-            int e_tau[K];
-            {
-                float bet1 = 0.f, bet2 = 0.f;
-#pragma unroll
-                for (int kk = K - 1; kk >= 1; --kk) {
-                    const float bet = xmax * hdr_s[1 + kk] + dmax2 * bet1 + bet2;
-                    const int e = (int)((__float_as_uint(bet) >> 23) & 0xffu) + 1;
-                    e_tau[kk] = max(30, min(240, e));
-                    bet2 = bet1;
-                    bet1 = bet;
-                }
-                e_tau[0] = 127;
-            }
+            if (!S_SPLIT) tile_scales();
             const uint64_t I2 = pk2(inv_si, inv_si);
             {
                 uint32_t v[16];
