@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
                 }
                 e_tau[0] = 127;
             };
-            if (S_SPLIT) tile_scales();
+            if (S_SPLIT && j > 0) tile_scales();   // (tile 0 is split by the compute warps themselves: see below)
             // ---- the tile's adjacency -> tensor memory (fp16 0 / 1 pairs), under the X W group
             {
                 uint2 m2v = make_uint2(0u, 0u);
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(384, 2) cheb_f16ws_kernel(const __grid_constan
             WPROBE(2);
             ph_mma ^= 1u;
             tc_fence_after();
-            if (!S_SPLIT) tile_scales();
+            if (!S_SPLIT || j == 0) tile_scales();   // every thread's share of the split precedes the X W group's issue
             const uint64_t I2 = pk2(inv_si, inv_si);
             {
                 uint32_t v[16];
