@@ -283,10 +283,10 @@ __global__ void grads_sum_stage2(const float* __restrict__ part, float* __restri
     out[p] = s;
 }
 
-// One-launch variant for parameter counts that are multiples of 4 (every 32-wide layer): float4 columns, 64 slices of
-// graphs summed with 8 loads in flight, and the LAST block of each column group (a self re-arming counter) adds the 64
+// One-launch variant for parameter counts that are multiples of 4 (every 32-wide layer): float4 columns, 32 slices of
+// graphs summed with 8 loads in flight, and the LAST block of each column group (a self re-arming counter) adds the 32
 // slice sums in slice order - the result does not depend on which block that is.
-#define MHO_SUM_SLICES4 64
+#define MHO_SUM_SLICES4 32
 __global__ void __launch_bounds__(128) grads_sum_fused(const float4* __restrict__ grads, float4* part, float4* __restrict__ out, unsigned int* counters,
                                                         int n_graphs, int n_params4) {
     const int col = blockIdx.x * 128 + threadIdx.x;
@@ -432,7 +432,7 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
             const int P4 = (int)(P / 4);
             const int nblk = (P4 + threads - 1) / threads;
             // scratch: one counter per column group (4 KB at a fixed place: zeroed when the slot is (re)allocated, self re-arming
-            // after that), then the 64 slice sums
+            // after that), then the slice sums
             const size_t cnt_bytes = 4096;
             if ((size_t)nblk * sizeof(unsigned int) > cnt_bytes) { mho_set_error("mho_cheb_backward: %lld parameters exceed the reduction's column groups", (long long)P); return MHO_ERR_TOO_LARGE; }
             const size_t need = cnt_bytes + (size_t)MHO_SUM_SLICES4 * P * sizeof(float);
