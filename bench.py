@@ -512,6 +512,30 @@ def run_gpu_arm(args):
             "ms_per_step": train_ms, "ms_per_step_one_stream": train1_ms, "streams": n_tr, "launches_per_step": train_launches / nt,
             "kernels": "cheb_f16ws_kernel (forward), cheb_backward_f16_kernel (tensor-core VJP), grads_sum_fused"}
         del gtt, gt1
+        # ---- the same for the model the reference ships and trains (AdHoc_train: 4-32-32-32-32-1, K=1): fused forward with kept
+        # activations (cheb_mlp_f16_kernel) + VJP of the stack (cheb_backward_kernel, CUDA cores) + gradient sum
+        nets5_t = [ChebNet(specs5, device=dev, private_context=True) for _ in range(n_tr)]
+        for n5_ in nets5_t:
+            n5_.set_flat(net5.get_flat())
+        dY5 = torch.randn((n_nodes, 1), device=dev)
+        keep5 = {}
+
+        def train_step5(i):
+            n5_ = nets5_t[i % n_tr]
+            Yt, saved = n5_.forward(batches[i % R], X5s[i % len(X5s)], save=True)
+            keep5[i % (2 * n_tr)] = n5_.backward(batches[i % R], X5s[i % len(X5s)], Yt, saved, dY5)
+        for i in range(max(R, 2 * n_tr) + 2):
+            train_step5(i)
+        barrier()
+        nt5 = max(4, min(args.steps, 12))
+        gt5 = GraphTimer(torch, dev, train_step5, nt5, n_tr, barrier)
+        train5_ms = float(np.median(gt5.run(max(3, replays // 2)))) / nt5
+        train5_ms = float(max_over_ranks([train5_ms])[0])
+        series["reference_stack_forward_backward_K1"] = {
+            "value": world * args.graphs / (train5_ms * 1e-3), "unit": "graph forward+VJP steps/s (per-graph gradients + their deterministic sum)",
+            "ms_per_step": train5_ms, "streams": n_tr,
+            "kernels": "cheb_mlp_f16_kernel (forward), cheb_backward_kernel (CUDA-core VJP of the 5-layer stack), grads_sum_stage1/2"}
+        del gt5
         # ---- gradient exchange of AdHoc_train (gnn_offloading_agent.py:156-169 site): NCCL on device tensors
         if world > 1:
             from multihop_offload_b200 import parallel
