@@ -378,8 +378,37 @@ extern "C" int mho_cheb_backward(mho_ctx_t* c, const mho_batch_t* b, const mho_l
     if ((b->rowptr_t == nullptr) != (b->colidx_t == nullptr)) { mho_set_error("mho_cheb_backward: rowptr_t/colidx_t must both be set or both NULL"); return MHO_ERR_INVALID; }
     if (b->max_tile_rows < 1) { mho_set_error("mho_cheb_backward: batch.max_tile_rows must be the largest graph"); return MHO_ERR_INVALID; }
 
-    const bool use_f16 = cheb_backward_f16_eligible(b, layers, n_layers, X, Y, dY, dX, c->max_smem_optin);
-    if (use_f16) {
+    bool use_f16 = cheb_backward_f16_eligible(b, layers, n_layers, X, Y, dY, dX, c->max_smem_optin);
+    if (!use_f16 && cheb_mlp_backward_eligible(b, layers, n_layers, X, saved, dX, c->max_smem_optin)) {
+        // K = 1 stack (the shipped model): tensor-core VJP with cached W^T images
+        LayerDev ld[MHO_MAX_LAYERS];
+        mho_fill_layers(layers, n_layers, b->total_nodes, ld);
+        bool same = c->wmb_valid && (int)c->wbkey.size() == n_layers;
+        for (int l = 0; same && l < n_layers; ++l) {
+            const mho_wkey k{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out};
+            same = k == c->wbkey[l];
+        }
+        if (!same) {
+            const size_t bytes = (size_t)cheb_mlp_backward_weight_bytes(n_layers);
+            if (bytes > c->wmb_bytes) {
+                if (c->wmb) cudaFree(c->wmb);
+                c->wmb = nullptr; c->wmb_bytes = 0;
+                if (cudaMalloc((void**)&c->wmb, bytes) != cudaSuccess) { mho_set_error("cudaMalloc(%zu) for prepared weights failed", bytes); return MHO_ERR_CUDA; }
+                c->wmb_bytes = bytes;
+            }
+            cudaError_t e = cudaMemsetAsync(c->wmb, 0, bytes, st);
+            if (e == cudaSuccess) e = prepare_mlp_backward_weights_launch(ld, n_layers, c->wmb, st);
+            if (e != cudaSuccess) { mho_set_error("prepare_mlp_backward_weights launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+            c->launches += 1;
+            c->wbkey.clear();
+            for (int l = 0; l < n_layers; ++l) c->wbkey.push_back(mho_wkey{layers[l].W, layers[l].b, layers[l].K, layers[l].f_in, layers[l].f_out});
+            c->wmb_valid = true;
+        }
+        cudaError_t e = cheb_mlp_backward_launch(b, ld, n_layers, X, Y, (const float*)saved, dY, grads_per_graph, (long long)P, c->wmb, c->num_sms, st);
+        if (e != cudaSuccess) { mho_set_error("cheb_mlp_backward launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
+        c->launches += 1;
+        use_f16 = true;   // (the per-graph rows are written: only the sum is left)
+    } else if (use_f16) {
         cudaError_t e = cheb_backward_f16_launch(b, layers, X, Y, dY, grads_per_graph, (long long)P, c->num_sms, st);
         if (e != cudaSuccess) { mho_set_error("cheb_backward_f16 launch failed: %s", cudaGetErrorString(e)); return MHO_ERR_CUDA; }
         c->launches += 1;

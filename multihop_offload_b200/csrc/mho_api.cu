@@ -75,6 +75,7 @@ extern "C" int mho_destroy(mho_ctx_t* c) {
     if (c->wdense) cudaFree(c->wdense);
     if (c->wf16) cudaFree(c->wf16);
     if (c->wmlp) cudaFree(c->wmlp);
+    if (c->wmb) cudaFree(c->wmb);
     if (c->sched) cudaFree(c->sched);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
@@ -110,7 +111,7 @@ extern "C" int mho_host_free(void* ptr) {
 extern "C" int64_t mho_launch_count(const mho_ctx_t* c) { return c ? c->launches : 0; }
 
 extern "C" int mho_invalidate_weights(mho_ctx_t* c) {
-    if (c) { c->wprep_valid = false; c->wdense_valid = false; c->wf16_valid = false; c->wmlp_valid = false; }
+    if (c) { c->wprep_valid = false; c->wdense_valid = false; c->wf16_valid = false; c->wmlp_valid = false; c->wmb_valid = false; }
     return MHO_OK;
 }
 

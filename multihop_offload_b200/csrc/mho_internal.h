@@ -48,6 +48,11 @@ struct mho_ctx {
     bool wmlp_valid = false;
     unsigned char* wmlp = nullptr;
     size_t wmlp_bytes = 0;
+    // fp16 W^T images of the K = 1 stack VJP (cheb_mlp_backward_f16.cu)
+    std::vector<mho_wkey> wbkey;
+    bool wmb_valid = false;
+    unsigned char* wmb = nullptr;
+    size_t wmb_bytes = 0;
     int* sched = nullptr;  // two zero-initialised ints: dynamic tile scheduler state (self re-arming)
     int device = 0;
     int num_sms = 0;
@@ -84,6 +89,12 @@ bool cheb_backward_f16_eligible(const mho_batch_t* b, const mho_layer_t* layers,
                                 const void* dX, int max_smem_optin);
 cudaError_t cheb_backward_f16_launch(const mho_batch_t* b, const mho_layer_t* layers, const float* X, const float* Y, const float* dY,
                                      float* grads, long long n_params, int num_sms, cudaStream_t st);
+bool cheb_mlp_backward_eligible(const mho_batch_t* b, const mho_layer_t* layers, int n_layers, const void* X, const void* saved, const void* dX,
+                                int max_smem_optin);
+int cheb_mlp_backward_weight_bytes(int n_layers);
+cudaError_t prepare_mlp_backward_weights_launch(const LayerDev* layers, int n_layers, unsigned char* out, cudaStream_t st);
+cudaError_t cheb_mlp_backward_launch(const mho_batch_t* b, const LayerDev* layers, int n_layers, const float* X, const float* Y, const float* saved,
+                                     const float* dY, float* grads, long long n_params, const unsigned char* wT, int num_sms, cudaStream_t st);
 cudaError_t apsp_launch(int n_graphs, const int32_t* node_off, const int32_t* rowptr, const int32_t* colidx, const double* weight,
                         const int64_t* out_off, double* dist, int max_smem_optin, cudaStream_t st);
 cudaError_t cheb_forward_launch(FwdParams& p, int max_tile_rows, int max_tile_nnz, int num_sms, int max_smem_optin,
