@@ -513,7 +513,7 @@ def run_gpu_arm(args):
             "kernels": "cheb_f16ws_kernel (forward), cheb_backward_f16_kernel (tensor-core VJP), grads_sum_fused"}
         del gtt, gt1
         # ---- the same for the model the reference ships and trains (AdHoc_train: 4-32-32-32-32-1, K=1): fused forward with kept
-        # activations (cheb_mlp_f16_kernel) + VJP of the stack (cheb_backward_kernel, CUDA cores) + gradient sum
+        # activations (cheb_mlp_f16_kernel) + VJP of the stack (cheb_mlp_backward_f16_kernel) + gradient sum
         nets5_t = [ChebNet(specs5, device=dev, private_context=True) for _ in range(n_tr)]
         for n5_ in nets5_t:
             n5_.set_flat(net5.get_flat())
@@ -534,7 +534,7 @@ def run_gpu_arm(args):
         series["reference_stack_forward_backward_K1"] = {
             "value": world * args.graphs / (train5_ms * 1e-3), "unit": "graph forward+VJP steps/s (per-graph gradients + their deterministic sum)",
             "ms_per_step": train5_ms, "streams": n_tr,
-            "kernels": "cheb_mlp_f16_kernel (forward), cheb_backward_kernel (CUDA-core VJP of the 5-layer stack), grads_sum_stage1/2"}
+            "kernels": "cheb_mlp_f16_kernel (forward), cheb_mlp_backward_f16_kernel (tensor-core VJP of the 5-layer stack), grads_sum_stage1/2"}
         del gt5
         # ---- gradient exchange of AdHoc_train (gnn_offloading_agent.py:156-169 site): NCCL on device tensors
         if world > 1:

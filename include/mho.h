@@ -155,7 +155,9 @@ size_t mho_saved_bytes(const mho_batch_t* batch, const mho_layer_t* layers, int3
  * all-reduce ships).  dX nullable.  Requires a one-graph-per-tile batch (tile_off == NULL).
  * One layer 32 -> 32, 2 <= K <= 10, vals == NULL, graphs of <= 128 nodes, dX == NULL and batch->adj_bits set (bit rows
  * relative to each GRAPH's first node: what mho_fill_adj_bits gives for tile_off = 0, 1, 2, ...) runs on the tensor
- * cores (csrc/cheb_backward_f16.cu); every other shape on csrc/cheb_backward.cu. */
+ * cores (csrc/cheb_backward_f16.cu); stacks whose layers all have K = 1, hidden width 32, first f_in a multiple of 4, last
+ * f_out <= 4 (the shipped model) with dX == NULL run on csrc/cheb_mlp_backward_f16.cu; every other shape on
+ * csrc/cheb_backward.cu. */
 int mho_cheb_backward(mho_ctx_t* ctx, const mho_batch_t* batch, const mho_layer_t* layers,
                       int32_t n_layers, const float* X, const float* Y, const void* saved,
                       const float* dY, float* grads_per_graph, float* grads_sum, float* dX,
