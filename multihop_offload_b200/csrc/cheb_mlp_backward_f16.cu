@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "mho_common.cuh"
 #include "mho_internal.h"
@@ -216,9 +217,11 @@ __global__ void __launch_bounds__(MB_THREADS, 2) cheb_mlp_backward_f16_kernel(co
     int node0 = 0, rows = 0;
     float* gout = p.grads;
 
-    for (int s = 0; s < n_items; ++s) {
+    // one item = one layer of one graph.  FULL: a 32 -> 32 layer (every predicate on the widths folds away)
+    auto item = [&](int s, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const int j = s / L, l = L - 1 - s % L;
-        const int fi = p.fi[l], fo = p.fo[l];
+        const int fi = FULL ? 32 : p.fi[l], fo = FULL ? 32 : p.fo[l];
         const uint32_t tile_a = t_a + (uint32_t)(s % 3) * HF_TILE_BYTES;
         if (l == L - 1) {
             // ---- a new graph: G of the last layer from dY and Y
@@ -371,6 +374,10 @@ __global__ void __launch_bounds__(MB_THREADS, 2) cheb_mlp_backward_f16_kernel(co
         }
         tc_fence_before();   // this thread's tensor-memory reads precede the next item's UMMAs (behind its barriers)
         MPROBE(9);
+    };
+    for (int s = 0; s < n_items; ++s) {
+        const int l = L - 1 - s % L;
+        if (p.fi[l] == 32 && p.fo[l] == 32) item(s, std::true_type{}); else item(s, std::false_type{});
     }
 #ifdef MHO_PROBE
     __syncthreads();
